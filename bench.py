@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- MAS cells/s (logp + DP + backtrack) on B200, next to the reference's CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4]
+
+One "step" = one pass of the hot path (models.py:362-382: log-likelihood matrix -> maximum_path
+-> dense path + durations) over one synthetic LJSpeech-shaped batch.  The default workload is the
+configuration BASELINE.json quotes the metric on for one GPU, configs[1]: fused logp+MAS for
+Glow-TTS base (80 mel channels), B=32, T_text=200, T_mel=1000, fp32, full lengths.  With N GPUs
+every rank processes its own batch of that shape (utterance sharding, no data-path collective):
+weak scaling, value = cells of all ranks / max-over-ranks device time.
+
+Printed JSON line (rank 0): the driver contract + ``roofline`` (dominant kernel, algorithmic bytes
+/ live CUDA-event time, vs MEASURED_PEAKS.json), ``cpu_baseline`` (the reference's CPU path timed
+on this box's host cores on a bounded sample), ``e2e`` (same metric through the public API from
+pinned HOST buffers, H2D + D2H inside the timed region), ``clocks`` and ``gpu_launches``.
+
+``--impl reference`` times the reference's own CPU implementation of the same step (its torch
+logp program on CPU + monotonic_align.maximum_path around its compiled OpenMP Cython kernel,
+oracle/_ref) and prints the same line with ``"impl": "reference"``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import __graft_entry__ as entry  # noqa: E402
+
+WORKLOADS = {
+    # name: (B per GPU, D, T_text, T_mel, description)
+    "c1": (32, 80, 200, 1000, "C1 standalone maximum_path B=32 T_text=200 T_mel=1000 fp32"),
+    "c2": (32, 80, 200, 1000, "C2 fused logp+MAS, Glow-TTS base (80 mels) B=32 T_text=200 T_mel=1000 fp32"),
+    "c3": (256, 80, 400, 2000, "C3 batch sweep B=256 T_text=400 T_mel=2000 fp32 (per GPU)"),
+    "c4": (8, 80, 1024, 8192, "C4 long-form B=8 T_text=1024 T_mel=8192 fp32"),
+}
+SEED = 1234  # the reference's config.seed (config.py:66)
+L2_BYTES = 126 * 2**20
+METRIC = "MAS cells/sec (logp+DP+backtrack)"
+UNIT = "cells/s"
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic inputs
+# ----------------------------------------------------------------------------------------------
+def synth_inputs(B, D, T_x, T_y, seed, mean_only=False):
+    """x_m ~ N(0,1), x_logs = 0.3 N(0,1) - 0.5 (general case; zeros when mean_only),
+    z = x_m[:, :, y*T_x/T_y] + exp(x_logs) N(0,1) ("trained-like"), full lengths."""
+    g = torch.Generator().manual_seed(seed)
+    x_m = torch.randn(B, D, T_x, generator=g)
+    x_logs = torch.zeros(B, D, T_x) if mean_only else 0.3 * torch.randn(B, D, T_x, generator=g) - 0.5
+    idx = (torch.arange(T_y) * T_x) // T_y
+    z = x_m[:, :, idx] + torch.exp(x_logs[:, :, idx]) * torch.randn(B, D, T_y, generator=g)
+    x_len = torch.full((B,), T_x, dtype=torch.int32)
+    y_len = torch.full((B,), T_y, dtype=torch.int32)
+    return x_m, x_logs, z, x_len, y_len
+
+
+def measured_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference arm (CPU)
+# ----------------------------------------------------------------------------------------------
+def reference_setup(B, D, T_x, T_y):
+    oracle = entry.load_oracle()
+    core = oracle.reference_core("omp")
+    kind = "reference"
+    if core is None:  # oracle/_ref never built: fall back to the C port of the same kernel
+        threads = oracle.host_threads()
+        kernel = lambda p, v, tx, ty: oracle.maximum_path_c(p, v, tx, ty, threads=threads)  # noqa: E731
+        kind = "port"
+    else:
+        kernel = core.maximum_path_c
+    cores = oracle.host_threads()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    torch.set_num_threads(cores)
+    x_m, x_logs, z, x_len, y_len = synth_inputs(B, D, T_x, T_y, SEED + 1)
+    x_mask = (torch.arange(T_x)[None] < x_len[:, None]).float()
+    z_mask = (torch.arange(T_y)[None] < y_len[:, None]).float()
+    attn_mask = x_mask[:, :, None] * z_mask[:, None, :]              # models.py:337 (squeezed)
+
+    def step():
+        return oracle.reference_step(x_m, x_logs, z, attn_mask, kernel=kernel)
+
+    return step, kind, cores
+
+
+def time_reference(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args):
+    B, D, T_x, T_y, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    step, kind, cores = reference_setup(B, D, T_x, T_y)
+    sec = time_reference(step, args.steps, args.warmup)
+    cells = B * T_x * T_y
+    value = cells / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "lengths": "full", "host": "CPU only: torch logp program (models.py:363-376) "
+                   "+ monotonic_align.maximum_path around the reference's OpenMP Cython kernel"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} full batches of the workload (B={B})"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm (GPU)
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    B, D, T_x, T_y, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # noqa: WPS433
+
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = entry.load_package()
+    assert pkg._lib.load().mas_b200_device_ok() == 0, "device is not sm_100 (B200)"
+    standalone = args.workload == "c1"
+
+    cells = B * T_x * T_y
+    in_bytes = 4 * B * D * (T_y + 2 * T_x) + 8 * B
+    out_bytes = 4 * cells + 4 * B * T_x
+    # ---- resident inputs, rotated so that consecutive steps never hit L2 ----
+    per_set = in_bytes + out_bytes + pkg._lib.load().mas_b200_fused_workspace_bytes(B, D, T_x, T_y)
+    n_sets = max(3, int(2.5 * L2_BYTES // per_set) + 1)
+    sets = []
+    for i in range(n_sets):
+        x_m, x_logs, z, x_len, y_len = synth_inputs(B, D, T_x, T_y, SEED + 1 + rank * 1000 + i)
+        sets.append(tuple(t.to(dev) for t in (x_m, x_logs, z, x_len, y_len)))
+    logp_sets = None
+    if standalone:
+        logp_sets = [(pkg.log_likelihood_matrix(s[0], s[1], s[2]), s[3], s[4]) for s in sets]
+
+    def step(i):
+        s = sets[i % n_sets]
+        if standalone:
+            lp, tx, ty = logp_sets[i % n_sets]
+            return pkg.maximum_path_from_lengths(lp, tx, ty, want_durations=True)
+        return pkg.fused_maximum_path(s[0], s[1], s[2], s[3], s[4])
+
+    launches_per_step = 1 if standalone else 2   # round-1: logp kernel + path kernel
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        out = step(args.warmup + i)
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+
+    # ---- dominant kernel alone: kernel (1) on materialised scores, rotated buffers ----
+    if logp_sets is None:
+        logp_sets = [(pkg.log_likelihood_matrix(s[0], s[1], s[2]), s[3], s[4]) for s in sets[:max(3, n_sets // 2)]]
+    for i in range(3):
+        lp, tx, ty = logp_sets[i % len(logp_sets)]
+        pkg.maximum_path_from_lengths(lp, tx, ty, want_durations=True)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(args.steps):
+        lp, tx, ty = logp_sets[i % len(logp_sets)]
+        pkg.maximum_path_from_lengths(lp, tx, ty, want_durations=True)
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / args.steps
+
+    # ---- end to end through the public API from pinned host buffers ----
+    host = [tuple(t.pin_memory() for t in synth_inputs(B, D, T_x, T_y, SEED + 77 + rank * 1000 + i)) for i in range(2)]
+    host_out = torch.empty((B, T_x, T_y), dtype=torch.float32).pin_memory()
+    host_dur = torch.empty((B, T_x), dtype=torch.int32).pin_memory()
+
+    def e2e_step(i):
+        x_m, x_logs, z, x_len, y_len = host[i % 2]
+        d = [t.to(dev, non_blocking=True) for t in (x_m, x_logs, z, x_len, y_len)]
+        path, dur = pkg.fused_maximum_path(*d)
+        host_out.copy_(path, non_blocking=True)
+        host_dur.copy_(dur, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the result
+
+    for i in range(max(2, args.warmup // 2)):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, args.steps // 4)
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = times.tolist()
+    value = world * cells * args.steps / (dev_ms * 1e-3)
+    e2e_value = world * cells * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        algo_bytes = 8 * cells                      # kernel (1): read fp32 scores + write fp32 path
+        achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tfile = REPO / "profiles" / "traffic.json"
+        if tfile.exists():
+            traffic = json.loads(tfile.read_text()).get(args.workload)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "per_gpu_batch": B, "global_batch": B * world, "lengths": "full",
+                       "channels": D, "parallelism": f"utterance-sharded x{world}, no collective",
+                       "l2": f"inputs/outputs rotated over {n_sets} buffer sets ({n_sets * per_set / 2**20:.0f} MiB > L2)",
+                       "kernels_per_step": launches_per_step},
+            "roofline": {"bound": "hbm", "kernel": "mas_path (kernel 1: DP + backtrack + dense path)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
+                         "kernel_ms": kern_ms, "peak_source": peak_src},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "clocks": clocks,
+            "gpu_launches": launches_per_step * args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ref_step, kind, cores = reference_setup(B, D, T_x, T_y)
+            ref_step()
+            reps, t0 = 0, time.perf_counter()
+            while reps < 3 or (time.perf_counter() - t0 < args.cpu_seconds and reps < 400):
+                ref_step()
+                reps += 1
+            sec = (time.perf_counter() - t0) / reps
+            line["cpu_baseline"] = {"value": cells / sec, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{reps} full batches (B={B}) of the same workload on the host, "
+                                              f"{sec * 1e3:.1f} ms each"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

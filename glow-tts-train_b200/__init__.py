@@ -1,0 +1,31 @@
+"""glow-tts-train_b200 -- B200-native (sm_100a) alignment hot path of Glow-TTS training.
+
+The directory name is not a Python identifier; import it through ``__graft_entry__.load_package()``
+(registers it as ``glow_tts_train_b200``) or put this directory's parent on ``sys.path`` and use
+``importlib``.  Contents:
+
+  monotonic_align   drop-in for ``glow_tts_train.monotonic_align`` (``maximum_path(value, mask)``)
+  alignment         the wider host API: fused logp+MAS, materialised logp, durations
+  _lib              ctypes binding of libmas_b200.so (the C ABI in include/mas_b200.h)
+  build             nvcc recipe for the library
+  csrc/             the CUDA kernels and the C-ABI layer
+
+There is no CPU fallback: without the compiled library or without a CUDA device every compute
+entry point raises.
+"""
+from . import _lib, alignment, monotonic_align  # noqa: F401
+from .alignment import (  # noqa: F401
+    fused_maximum_path,
+    log_likelihood_matrix,
+    maximum_path_from_lengths,
+)
+from .monotonic_align import maximum_path  # noqa: F401
+
+__all__ = [
+    "maximum_path",
+    "maximum_path_from_lengths",
+    "fused_maximum_path",
+    "log_likelihood_matrix",
+    "monotonic_align",
+    "alignment",
+]

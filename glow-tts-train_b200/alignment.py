@@ -1,0 +1,140 @@
+"""Host API of the alignment hot path (Python/PyTorch above the C ABI).
+
+PyTorch is used for device memory, streams and dtype plumbing only; every arithmetic step runs in
+the sm_100a kernels of libmas_b200.so.  All entry points are asynchronous on the current torch CUDA
+stream of the inputs' device and never synchronise the host.
+
+Reference call sites replaced (rhasspy/glow-tts-train):
+  glow_tts_train/models.py:362-376   -> log_likelihood_matrix
+  glow_tts_train/models.py:362-382   -> fused_maximum_path        (+ :393 durations)
+  glow_tts_train/monotonic_align/core.pyx:40-45 -> maximum_path_from_lengths
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the alignment path has no CPU implementation")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def maximum_path_from_lengths(value, t_x=None, t_y=None, *, mask=None, want_durations=False,
+                              want_frame_token=False, max_neg_val=_lib.MAX_NEG_VAL):
+    """Kernel (1).  ``value`` fp32 CUDA [B,T_x,T_y] (frame stride 1); lengths either as int32 CUDA
+    vectors ``t_x``/``t_y`` or read on the device from ``mask`` (fp32 CUDA, any strides) the way
+    monotonic_align/__init__.py:18-19 does.  Returns ``path`` fp32 [B,T_x,T_y] (and optionally
+    int32 ``durations`` [B,T_x], ``frame_token`` [B,T_y])."""
+    lib = _lib.load()
+    _require_cuda(value, "value")
+    if value.dtype != torch.float32 or value.dim() != 3:
+        raise TypeError("value must be a float32 [B, T_x, T_y] tensor")
+    if value.stride(2) != 1 and value.numel() > 0:
+        value = value.contiguous()
+    B, T_x, T_y = value.shape
+    dev = value.device
+    if (t_x is None) != (t_y is None):
+        raise ValueError("pass both t_x and t_y, or neither (and a mask)")
+    if t_x is None:
+        if mask is None:
+            raise ValueError("lengths or mask required")
+        _require_cuda(mask, "mask")
+        if mask.dtype != torch.float32 or tuple(mask.shape) != (B, T_x, T_y) or mask.device != dev:
+            raise TypeError("mask must be float32 with value's shape and device")
+        ms = mask.stride()
+    else:
+        for name, t in (("t_x", t_x), ("t_y", t_y)):
+            if t.dtype != torch.int32 or t.device != dev or t.shape != (B,) or not t.is_contiguous():
+                raise TypeError(f"{name} must be a contiguous int32 [B] tensor on value's device")
+        ms = (0, 0, 0)
+        mask = None
+    path = torch.empty((B, T_x, T_y), dtype=torch.float32, device=dev)
+    durations = torch.empty((B, T_x), dtype=torch.int32, device=dev) if want_durations else None
+    frame_token = torch.empty((B, T_y), dtype=torch.int32, device=dev) if want_frame_token else None
+    if path.numel() == 0:
+        return _pack(path, durations, frame_token)
+    ws = _workspace(lib.mas_b200_workspace_bytes(B, T_x, T_y), dev)
+    with torch.cuda.device(dev):
+        rc = lib.mas_b200_maximum_path_f32(
+            value.data_ptr(), value.stride(0), value.stride(1), _ptr(t_x), _ptr(t_y),
+            _ptr(mask), ms[0], ms[1], ms[2], path.data_ptr(), _ptr(durations), _ptr(frame_token),
+            ws.data_ptr(), ws.numel(), B, T_x, T_y, max_neg_val, _stream(dev))
+    _lib.check(rc, "mas_b200_maximum_path_f32")
+    return _pack(path, durations, frame_token)
+
+
+def _pack(path, durations, frame_token):
+    extra = tuple(t for t in (durations, frame_token) if t is not None)
+    return (path, *extra) if extra else path
+
+
+def _check_prior(x_m, x_logs, z):
+    for name, t in (("x_m", x_m), ("z", z)) + ((("x_logs", x_logs),) if x_logs is not None else ()):
+        _require_cuda(t, name)
+        if t.dtype != torch.float32 or t.dim() != 3:
+            raise TypeError(f"{name} must be a float32 [B, D, T] tensor")
+    B, D, T_x = x_m.shape
+    if z.shape[0] != B or z.shape[1] != D or (x_logs is not None and x_logs.shape != x_m.shape):
+        raise ValueError("x_m / x_logs [B,D,T_x] and z [B,D,T_y] disagree")
+    return B, D, T_x, z.shape[2]
+
+
+def log_likelihood_matrix(x_m, x_logs, z):
+    """models.py:362-376 on the GPU: ``x_m``/``x_logs`` [B,D,T_x] (``x_logs=None`` == zeros, the
+    mean_only configuration), ``z`` [B,D,T_y] -> logp fp32 [B,T_x,T_y]."""
+    lib = _lib.load()
+    B, D, T_x, T_y = _check_prior(x_m, x_logs, z)
+    x_m, z = x_m.contiguous(), z.contiguous()
+    x_logs = x_logs.contiguous() if x_logs is not None else None
+    out = torch.empty((B, T_x, T_y), dtype=torch.float32, device=x_m.device)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(x_m.device):
+        rc = lib.mas_b200_logp_f32(x_m.data_ptr(), _ptr(x_logs), z.data_ptr(), out.data_ptr(),
+                                   B, D, T_x, T_y, _stream(x_m.device))
+    _lib.check(rc, "mas_b200_logp_f32")
+    return out
+
+
+def fused_maximum_path(x_m, x_logs, z, x_lengths, y_lengths, *, want_durations=True,
+                       want_frame_token=False, max_neg_val=_lib.MAX_NEG_VAL):
+    """Kernel (2): models.py:362-382 in one call, the score matrix never leaves the chip.
+    ``x_lengths``/``y_lengths`` are the integer lengths the prefix masks of models.py:334-337
+    encode (``y_lengths`` already floored to n_sqz, models.py:405).  Returns ``path`` fp32
+    [B,T_x,T_y] (+ int32 ``durations`` [B,T_x], ``frame_token`` [B,T_y] on request)."""
+    lib = _lib.load()
+    B, D, T_x, T_y = _check_prior(x_m, x_logs, z)
+    dev = x_m.device
+    x_m, z = x_m.contiguous(), z.contiguous()
+    x_logs = x_logs.contiguous() if x_logs is not None else None
+    x_len = x_lengths.to(device=dev, dtype=torch.int32).contiguous()
+    y_len = y_lengths.to(device=dev, dtype=torch.int32).contiguous()
+    if x_len.shape != (B,) or y_len.shape != (B,):
+        raise ValueError("x_lengths / y_lengths must have shape [B]")
+    path = torch.empty((B, T_x, T_y), dtype=torch.float32, device=dev)
+    durations = torch.empty((B, T_x), dtype=torch.int32, device=dev) if want_durations else None
+    frame_token = torch.empty((B, T_y), dtype=torch.int32, device=dev) if want_frame_token else None
+    if path.numel() == 0:
+        return _pack(path, durations, frame_token)
+    ws = _workspace(lib.mas_b200_fused_workspace_bytes(B, D, T_x, T_y), dev)
+    with torch.cuda.device(dev):
+        rc = lib.mas_b200_fused_maximum_path_f32(
+            x_m.data_ptr(), _ptr(x_logs), z.data_ptr(), x_len.data_ptr(), y_len.data_ptr(),
+            path.data_ptr(), _ptr(durations), _ptr(frame_token), ws.data_ptr(), ws.numel(),
+            B, D, T_x, T_y, max_neg_val, _stream(dev))
+    _lib.check(rc, "mas_b200_fused_maximum_path_f32")
+    return _pack(path, durations, frame_token)

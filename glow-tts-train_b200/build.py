@@ -1,0 +1,72 @@
+"""Build libmas_b200.so (the C-ABI library of include/mas_b200.h) in-tree with nvcc for sm_100a.
+
+    python glow-tts-train_b200/build.py [--force] [--verbose]
+
+nvcc cross-compiles without a GPU; the resulting .so sits next to this file so that it travels to
+the GPU box with the repository snapshot.  cudart is linked statically (nvcc default), so the
+library has no dependency on torch or on a particular libcudart.so at run time.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO = PKG_DIR.parent
+CSRC = PKG_DIR / "csrc"
+INCLUDE = REPO / "include"
+LIB_PATH = PKG_DIR / "libmas_b200.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+    # bit-exactness: no fast-math, no flush-to-zero, IEEE div/sqrt (these are the defaults; spelled
+    # out so nobody "optimises" them away).  FMA contraction is left on: the DP has no a*b+c
+    # pattern, and the logp contraction uses explicit fmaf().
+    "--ftz=false", "--prec-div=true", "--prec-sqrt=true",
+]
+
+
+def find_nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def sources() -> list[Path]:
+    return sorted(CSRC.glob("*.cu"))
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h")) + [Path(__file__)]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [find_nvcc(), *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}"]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    tmp = LIB_PATH.with_suffix(".so.tmp")
+    cmd += ["-o", str(tmp), *map(str, sources())]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+    if proc.returncode != 0:
+        tmp.unlink(missing_ok=True)
+        raise RuntimeError(f"nvcc failed ({proc.returncode}): {' '.join(cmd)}")
+    tmp.replace(LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,210 @@
+// mas_api.cu -- the extern "C" surface declared in include/mas_b200.h: argument validation,
+// workspace carving and kernel dispatch.  No torch, no exceptions, no host synchronisation
+// (except mas_b200_maximum_path_host_i32, which is synchronous by contract).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "mas_kernels.cuh"
+
+namespace mas {
+thread_local int g_last_cuda_error = 0;
+}
+
+using namespace mas;
+
+namespace {
+
+struct FusedWorkspace {
+    size_t logp_bytes, path_ws_bytes;
+};
+
+FusedWorkspace fused_ws(int B, int T_x, int T_y) {
+    FusedWorkspace w;
+    w.logp_bytes = align_up((size_t)B * T_x * T_y * sizeof(float), 256);
+    w.path_ws_bytes = path_simple_workspace_bytes(B, T_x, T_y);
+    return w;
+}
+
+bool shape_ok(int B, int T_x, int T_y) {
+    return B >= 0 && T_x >= 0 && T_y >= 0 && T_x <= MAS_B200_MAX_TOKENS && T_y <= MAS_B200_MAX_FRAMES;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mas_b200_abi_version(void) { return MAS_B200_ABI_VERSION; }
+
+const char *mas_b200_status_string(int status) {
+    switch (status) {
+        case MAS_OK: return "ok";
+        case MAS_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case MAS_ERR_UNSUPPORTED_SHAPE: return "unsupported shape";
+        case MAS_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+        case MAS_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+        case MAS_ERR_CUDA: return "CUDA error";
+        case MAS_ERR_BAD_LENGTHS: return "bad utterance lengths";
+        default: return "unknown status";
+    }
+}
+
+int mas_b200_last_cuda_error(void) { return g_last_cuda_error; }
+
+int mas_b200_device_ok(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return MAS_ERR_NO_DEVICE;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+        return MAS_ERR_NO_DEVICE;
+    return major == 10 ? MAS_OK : MAS_ERR_NO_DEVICE;
+}
+
+size_t mas_b200_workspace_bytes(int B, int T_x, int T_y) {
+    if (!shape_ok(B, T_x, T_y)) return 0;
+    return path_simple_workspace_bytes(B, T_x, T_y);
+}
+
+size_t mas_b200_fused_workspace_bytes(int B, int D, int T_x, int T_y) {
+    (void)D;
+    if (!shape_ok(B, T_x, T_y)) return 0;
+    FusedWorkspace w = fused_ws(B, T_x, T_y);
+    return w.logp_bytes + w.path_ws_bytes;
+}
+
+int mas_b200_maximum_path_f32(const float *value, int64_t value_stride_b, int64_t value_stride_x,
+                              const int32_t *t_x, const int32_t *t_y,
+                              const float *mask, int64_t mask_stride_b, int64_t mask_stride_x,
+                              int64_t mask_stride_y,
+                              float *path, int32_t *durations, int32_t *frame_token,
+                              void *workspace, size_t workspace_bytes,
+                              int B, int T_x, int T_y, float max_neg_val, mas_stream_t stream) {
+    if (!shape_ok(B, T_x, T_y)) return (B < 0 || T_x < 0 || T_y < 0) ? MAS_ERR_INVALID_ARGUMENT : MAS_ERR_UNSUPPORTED_SHAPE;
+    if (B == 0 || T_x == 0 || T_y == 0) return MAS_OK;
+    if (value == nullptr || path == nullptr) return MAS_ERR_INVALID_ARGUMENT;
+    if ((t_x == nullptr) != (t_y == nullptr)) return MAS_ERR_INVALID_ARGUMENT;
+    if (t_x == nullptr && mask == nullptr) return MAS_ERR_INVALID_ARGUMENT;
+    if (value_stride_x < T_y || value_stride_b < 0) return MAS_ERR_INVALID_ARGUMENT;
+    PathParams p{};
+    p.value = value;
+    p.value_stride_b = value_stride_b;
+    p.value_stride_x = value_stride_x;
+    p.t_x = t_x;
+    p.t_y = t_y;
+    p.mask = mask;
+    p.mask_stride_b = mask_stride_b;
+    p.mask_stride_x = mask_stride_x;
+    p.mask_stride_y = mask_stride_y;
+    p.path = path;
+    p.durations = durations;
+    p.frame_token = frame_token;
+    p.B = B;
+    p.T_x = T_x;
+    p.T_y = T_y;
+    p.max_neg_val = max_neg_val;
+    return launch_path_simple(p, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_logp_f32(const float *x_m, const float *x_logs, const float *z, float *logp,
+                      int B, int D, int T_x, int T_y, mas_stream_t stream) {
+    if (B < 0 || D < 0 || T_x < 0 || T_y < 0) return MAS_ERR_INVALID_ARGUMENT;
+    if (!shape_ok(B, T_x, T_y) || D > MAS_B200_MAX_CHANNELS) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (B == 0 || T_x == 0 || T_y == 0) return MAS_OK;
+    if (x_m == nullptr || z == nullptr || logp == nullptr) return MAS_ERR_INVALID_ARGUMENT;
+    LogpParams p{x_m, x_logs, z, logp, B, D, T_x, T_y};
+    return launch_logp(p, static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_fused_maximum_path_f32(const float *x_m, const float *x_logs, const float *z,
+                                    const int32_t *x_len, const int32_t *y_len,
+                                    float *path, int32_t *durations, int32_t *frame_token,
+                                    void *workspace, size_t workspace_bytes,
+                                    int B, int D, int T_x, int T_y, float max_neg_val,
+                                    mas_stream_t stream) {
+    if (B < 0 || D < 0 || T_x < 0 || T_y < 0) return MAS_ERR_INVALID_ARGUMENT;
+    if (!shape_ok(B, T_x, T_y) || D > MAS_B200_MAX_CHANNELS) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (B == 0 || T_x == 0 || T_y == 0) return MAS_OK;
+    if (x_m == nullptr || z == nullptr || path == nullptr || x_len == nullptr || y_len == nullptr)
+        return MAS_ERR_INVALID_ARGUMENT;
+    FusedWorkspace w = fused_ws(B, T_x, T_y);
+    if (workspace == nullptr || workspace_bytes < w.logp_bytes + w.path_ws_bytes) return MAS_ERR_WORKSPACE_TOO_SMALL;
+    // ROUND-1 STATE: two launches (score matrix staged in the workspace, L2-resident for the
+    // training shapes).  The single-kernel variant replaces this body; the ABI does not change.
+    float *logp = static_cast<float *>(workspace);
+    int rc = mas_b200_logp_f32(x_m, x_logs, z, logp, B, D, T_x, T_y, stream);
+    if (rc != MAS_OK) return rc;
+    return mas_b200_maximum_path_f32(logp, (int64_t)T_x * T_y, T_y, x_len, y_len, nullptr, 0, 0, 0, path,
+                                     durations, frame_token, static_cast<unsigned char *>(workspace) + w.logp_bytes,
+                                     workspace_bytes - w.logp_bytes, B, T_x, T_y, max_neg_val, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer entry: staging buffers are cached per device and grown on demand.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct HostStage {
+    void *d_value = nullptr, *d_path = nullptr, *d_len = nullptr, *d_ws = nullptr;
+    size_t value_cap = 0, path_cap = 0, len_cap = 0, ws_cap = 0;
+    cudaStream_t stream = nullptr;
+};
+std::mutex g_stage_mutex;
+HostStage g_stage[64];
+
+int grow(void **ptr, size_t *cap, size_t need) {
+    if (need <= *cap) return MAS_OK;
+    if (*ptr) MAS_CUDA_TRY(cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    MAS_CUDA_TRY(cudaMalloc(ptr, need));
+    *cap = need;
+    return MAS_OK;
+}
+
+__global__ void path_f32_to_i32_kernel(const float *__restrict__ in, int32_t *__restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (int32_t)in[i];
+}
+}  // namespace
+
+int mas_b200_maximum_path_host_i32(int32_t *paths, const float *values, const int32_t *t_xs,
+                                   const int32_t *t_ys, int B, int T_x, int T_y,
+                                   float max_neg_val, int device) {
+    if (!shape_ok(B, T_x, T_y)) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (B == 0 || T_x == 0 || T_y == 0) return MAS_OK;
+    if (!paths || !values || !t_xs || !t_ys || device < 0 || device >= 64) return MAS_ERR_INVALID_ARGUMENT;
+    for (int b = 0; b < B; ++b)
+        if (t_xs[b] < 0 || t_ys[b] < 0 || t_xs[b] > T_x || t_ys[b] > T_y || t_xs[b] > t_ys[b]) return MAS_ERR_BAD_LENGTHS;
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    int prev_dev = 0;
+    MAS_CUDA_TRY(cudaGetDevice(&prev_dev));
+    MAS_CUDA_TRY(cudaSetDevice(device));
+    HostStage &s = g_stage[device];
+    int rc = MAS_OK;
+    const size_t cells = (size_t)B * T_x * T_y;
+    do {
+        if (!s.stream && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { rc = cuda_fail(cudaGetLastError()); break; }
+        // the fp32 path and the int32 result share one buffer pair: value | path(f32) -> path(i32) reuses value
+        if ((rc = grow(&s.d_value, &s.value_cap, cells * 4)) != MAS_OK) break;
+        if ((rc = grow(&s.d_path, &s.path_cap, cells * 4)) != MAS_OK) break;
+        if ((rc = grow(&s.d_len, &s.len_cap, (size_t)B * 8)) != MAS_OK) break;
+        if ((rc = grow(&s.d_ws, &s.ws_cap, mas_b200_workspace_bytes(B, T_x, T_y) + 256)) != MAS_OK) break;
+        int32_t *d_tx = static_cast<int32_t *>(s.d_len), *d_ty = d_tx + B;
+        cudaError_t e;
+        if ((e = cudaMemcpyAsync(s.d_value, values, cells * 4, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(d_tx, t_xs, (size_t)B * 4, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(d_ty, t_ys, (size_t)B * 4, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) { rc = cuda_fail(e); break; }
+        rc = mas_b200_maximum_path_f32(static_cast<float *>(s.d_value), (int64_t)T_x * T_y, T_y, d_tx, d_ty, nullptr, 0, 0, 0,
+                                       static_cast<float *>(s.d_path), nullptr, nullptr, s.d_ws, s.ws_cap, B, T_x, T_y,
+                                       max_neg_val, s.stream);
+        if (rc != MAS_OK) break;
+        // int32 result written over the (no longer needed) staged scores
+        path_f32_to_i32_kernel<<<148 * 4, 256, 0, s.stream>>>(static_cast<float *>(s.d_path), static_cast<int32_t *>(s.d_value), cells);
+        if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e); break; }
+        if ((e = cudaMemcpyAsync(paths, s.d_value, cells * 4, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) { rc = cuda_fail(e); break; }
+        if ((e = cudaStreamSynchronize(s.stream)) != cudaSuccess) { rc = cuda_fail(e); break; }
+    } while (false);
+    cudaSetDevice(prev_dev);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+// mas_kernels.cuh -- parameter blocks and launchers shared by the C-ABI layer (mas_api.cu).
+#pragma once
+
+#include "mas_common.cuh"
+
+namespace mas {
+
+// Kernel (1) arguments (see mas_b200_maximum_path_f32 in include/mas_b200.h).
+struct PathParams {
+    const float *value;
+    int64_t value_stride_b, value_stride_x;
+    const int32_t *t_x, *t_y;  // both null -> lengths from the mask
+    const float *mask;
+    int64_t mask_stride_b, mask_stride_x, mask_stride_y;
+    float *path;
+    int32_t *durations;    // nullable
+    int32_t *frame_token;  // nullable
+    uint32_t *ws_bits;     // workspace: packed direction bits [B][ceil(T_y/32)][T_x]
+    int32_t *ws_tok;       // workspace: frame -> token [B][T_y] when frame_token is null
+    int B, T_x, T_y;
+    float max_neg_val;
+};
+
+// Log-likelihood matrix arguments (mas_b200_logp_f32).
+struct LogpParams {
+    const float *x_m, *x_logs, *z;  // x_logs nullable (mean_only)
+    float *logp;
+    int B, D, T_x, T_y;
+};
+
+size_t path_simple_workspace_bytes(int B, int T_x, int T_y);
+int launch_path_simple(PathParams p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
+int launch_logp(const LogpParams &p, cudaStream_t stream);
+
+}  // namespace mas

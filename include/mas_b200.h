@@ -1,0 +1,141 @@
+/*
+ * mas_b200.h -- C ABI of the B200-native (sm_100a) alignment hot path of Glow-TTS training.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain device/host
+ * pointers, sizes and a CUDA stream handle (no torch types), never throws, never synchronises the
+ * host (except the *_host convenience entry), and returns an `int` status (MAS_OK == 0).
+ * The library is libmas_b200.so, built by nvcc for sm_100a from glow-tts-train_b200/csrc/.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree, rhasspy/glow-tts-train 0.3.0):
+ *   glow_tts_train/monotonic_align/core.pyx:40-45     maximum_path_c(paths, values, t_xs, t_ys, max_neg_val)
+ *   glow_tts_train/monotonic_align/core.pyx:9-35      maximum_path_each (forward DP + backtrack)
+ *   glow_tts_train/monotonic_align/__init__.py:18-19  t_x / t_y derived from the mask
+ *   glow_tts_train/models.py:362-376                  the [B,T_x,T_y] log-likelihood matrix
+ *   glow_tts_train/models.py:378-382                  logp -> maximum_path -> attn
+ *   glow_tts_train/models.py:393                      token durations (row sums of the path)
+ *
+ * Vocabulary: an *utterance* b has t_x[b] text tokens (rows, index x) and t_y[b] mel frames
+ * (columns, index y).  A *cell* is one (token, frame) pair; cells = B*T_x*T_y is the unit of the
+ * throughput metric.  All tensors are row-major with the frame index contiguous.
+ */
+#ifndef MAS_B200_H_
+#define MAS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAS_B200_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define MAS_OK 0
+#define MAS_ERR_INVALID_ARGUMENT 1   /* null pointer, negative size, bad stride ...               */
+#define MAS_ERR_UNSUPPORTED_SHAPE 2  /* T_x / T_y / D beyond what the kernels are built for       */
+#define MAS_ERR_WORKSPACE_TOO_SMALL 3
+#define MAS_ERR_NO_DEVICE 4          /* no CUDA device, or device is not sm_100 (B200)            */
+#define MAS_ERR_CUDA 5               /* a CUDA runtime/driver call failed: mas_b200_last_cuda_error() */
+#define MAS_ERR_BAD_LENGTHS 6        /* (host entry only) some t_x > t_y or t_x > T_x ...          */
+
+/* limits of this build */
+#define MAS_B200_MAX_TOKENS 2048     /* T_x  */
+#define MAS_B200_MAX_FRAMES 65536    /* T_y  */
+#define MAS_B200_MAX_CHANNELS 256    /* D    */
+
+/* The reference's "minus infinity" (core.pyx:40 default argument). */
+#define MAS_B200_MAX_NEG_VAL (-1e9f)
+
+/* opaque CUDA stream handle (cudaStream_t / CUstream); NULL = legacy default stream */
+typedef void *mas_stream_t;
+
+int mas_b200_abi_version(void);
+const char *mas_b200_status_string(int status);
+/* cudaError_t of the last failing CUDA call made by this library on the calling thread (0 if none) */
+int mas_b200_last_cuda_error(void);
+/* MAS_OK iff the current CUDA device can run the kernels (compute capability 10.x). */
+int mas_b200_device_ok(void);
+
+/*
+ * Scratch needed by the entry points below for a batch of shape (B, T_x, T_y): packed backtrack
+ * direction bits that do not fit in shared memory, per-utterance lengths, ... .  Caller-owned,
+ * device memory, 256-byte aligned, contents undefined before and after a call.  May return 0.
+ */
+size_t mas_b200_workspace_bytes(int B, int T_x, int T_y);
+/* Same for mas_b200_fused_maximum_path_f32 (never smaller than the above). */
+size_t mas_b200_fused_workspace_bytes(int B, int D, int T_x, int T_y);
+
+/*
+ * Kernel (1): monotonic alignment search on a materialised score matrix.
+ * Replaces maximum_path_c (core.pyx:40-45) together with the mask handling of
+ * monotonic_align/__init__.py:11,18-19.
+ *
+ *   value      [B][T_x][T_y] fp32 device, frame index contiguous; utterance/token strides in
+ *              ELEMENTS (value_stride_b, value_stride_x).  NOT modified (the reference clobbers
+ *              its private copy; there is no copy here).
+ *   t_x, t_y   int32 [B] device, per-utterance valid sizes; or both NULL, in which case
+ *   mask       [B][T_x][T_y] fp32 device (any strides, in elements) supplies them the reference's
+ *              way: t_x[b] = sum_x mask[b,x,0], t_y[b] = sum_y mask[b,0,y] (__init__.py:18-19).
+ *              Only that column/row of the mask is read: for the prefix masks models.py:334-337
+ *              builds, value*mask equals value on every cell the algorithm touches.
+ *   path       [B][T_x][T_y] fp32 device, contiguous: written completely (zeros and ones).
+ *   durations  int32 [B][T_x] device or NULL: frames per token (row sums of path; models.py:393).
+ *   frame_token int32 [B][T_y] device or NULL: token index of every frame, -1 for y >= t_y[b].
+ *   max_neg_val the reference's -1e9.
+ *
+ * Semantics are bit-exact with the reference for 1 <= t_x <= t_y (tie -> stay on the token,
+ * strict '>' / '<' compares, -1e9 boundary, fp32 round-to-nearest adds).  Defined behaviour where
+ * the reference has none: t_x == 0 or t_y == 0 -> all-zero path for that utterance; t_x > t_y ->
+ * treated as t_x = t_y (first t_y tokens on the diagonal).  Asynchronous on `stream`.
+ */
+int mas_b200_maximum_path_f32(const float *value, int64_t value_stride_b, int64_t value_stride_x,
+                              const int32_t *t_x, const int32_t *t_y,
+                              const float *mask, int64_t mask_stride_b, int64_t mask_stride_x,
+                              int64_t mask_stride_y,
+                              float *path, int32_t *durations, int32_t *frame_token,
+                              void *workspace, size_t workspace_bytes,
+                              int B, int T_x, int T_y, float max_neg_val, mas_stream_t stream);
+
+/*
+ * The log-likelihood matrix of models.py:362-376, materialised (used for tolerance tests and as
+ * the unfused pipeline stage):
+ *   logp[b,x,y] = sum_d(-0.5*log(2pi) - logs[b,d,x]) + sum_d exp(-2 logs[b,d,x]) * (-0.5 z[b,d,y]^2)
+ *               + sum_d (m[b,d,x] exp(-2 logs[b,d,x])) * z[b,d,y] + sum_d -0.5 m[b,d,x]^2 exp(-2 logs[b,d,x])
+ * summed as ((l1+l2)+l3)+l4 in fp32 (FFMA contraction over channels, ascending d).
+ *   x_m, x_logs [B][D][T_x] fp32 device contiguous; x_logs NULL == zeros (mean_only, config.py:52)
+ *   z           [B][D][T_y] fp32 device contiguous
+ *   logp        [B][T_x][T_y] fp32 device contiguous
+ */
+int mas_b200_logp_f32(const float *x_m, const float *x_logs, const float *z, float *logp,
+                      int B, int D, int T_x, int T_y, mas_stream_t stream);
+
+/*
+ * Kernel (2): fused log-likelihood + alignment search; the [B,T_x,T_y] score matrix is never
+ * written to memory.  Replaces models.py:362-382 (+ :393 through `durations`).
+ *   x_len, y_len int32 [B] device: valid tokens / frames (what the prefix masks encode).
+ * Other arguments as above.  logp tiles are accurate to 1e-5 relative against the fp64 formula;
+ * the path equals kernel (1) run on mas_b200_logp_f32's output bit for bit.
+ */
+int mas_b200_fused_maximum_path_f32(const float *x_m, const float *x_logs, const float *z,
+                                    const int32_t *x_len, const int32_t *y_len,
+                                    float *path, int32_t *durations, int32_t *frame_token,
+                                    void *workspace, size_t workspace_bytes,
+                                    int B, int D, int T_x, int T_y, float max_neg_val,
+                                    mas_stream_t stream);
+
+/*
+ * Host-buffer convenience used for end-to-end timing and by non-torch callers: takes HOST
+ * pointers with the layout of maximum_path_c (core.pyx:40) -- values fp32 [B][T_x][T_y]
+ * C-contiguous (NOT clobbered), t_xs / t_ys int32 [B], paths int32 [B][T_x][T_y] (fully written)
+ * -- stages them through device memory owned by the library on `device`, runs kernel (1) and
+ * returns after the result is in `paths`.  Synchronous.
+ */
+int mas_b200_maximum_path_host_i32(int32_t *paths, const float *values, const int32_t *t_xs,
+                                   const int32_t *t_ys, int B, int T_x, int T_y,
+                                   float max_neg_val, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAS_B200_H_ */

@@ -224,3 +224,24 @@ def logp_f32(x_m, x_logs, z) -> np.ndarray:
 def durations_from_path(path: np.ndarray) -> np.ndarray:
     """Per-token frame counts: row sums of the path (models.py:393 takes log(1e-8 + this))."""
     return np.asarray(path).sum(-1).astype(np.int32)
+
+
+def logp_torch(x_m, x_logs, z):
+    """The reference's own tensor program for the log-likelihood matrix, models.py:363-376, term by
+    term with torch ops (on whatever device the inputs live on; the CPU baseline runs it on CPU)."""
+    import math
+
+    import torch
+
+    with torch.no_grad():                                                         # models.py:362
+        x_s_sq_r = torch.exp(-2 * x_logs)                                         # :363
+        logp1 = torch.sum(-0.5 * math.log(2 * math.pi) - x_logs, [1]).unsqueeze(-1)   # :364-366
+        logp2 = torch.matmul(x_s_sq_r.transpose(1, 2), -0.5 * (z ** 2))           # :367-369
+        logp3 = torch.matmul((x_m * x_s_sq_r).transpose(1, 2), z)                 # :370-372
+        logp4 = torch.sum(-0.5 * (x_m ** 2) * x_s_sq_r, [1]).unsqueeze(-1)        # :373-375
+        return logp1 + logp2 + logp3 + logp4                                      # :376
+
+
+def reference_step(x_m, x_logs, z, attn_mask, kernel=None):
+    """models.py:362-382 as the reference runs it: logp_torch -> maximum_path(logp, mask)."""
+    return reference_boundary(logp_torch(x_m, x_logs, z), attn_mask, kernel=kernel)

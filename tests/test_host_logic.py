@@ -1,0 +1,121 @@
+"""Host-side logic that needs no GPU: the no-fallback guarantee, utterance sharding, and the N>1
+data path (world_size-2 gloo run on CPU)."""
+from __future__ import annotations
+
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def test_no_cpu_fallback(pkg):
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    v, m = torch.zeros(1, 3, 5), torch.ones(1, 3, 5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.monotonic_align.maximum_path(v, m)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        pkg.maximum_path_from_lengths(v, torch.ones(1, dtype=torch.int32), torch.ones(1, dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        pkg.fused_maximum_path(torch.zeros(1, 80, 3), None, torch.zeros(1, 80, 5), torch.tensor([3]), torch.tensor([5]))
+
+
+def test_product_does_not_import_oracle():
+    """The product path may not route through the oracle (or the reference) in any form."""
+    for path in (REPO / "glow-tts-train_b200").rglob("*"):
+        if path.suffix in {".py", ".cu", ".cuh", ".h"}:
+            text = path.read_text()
+            assert "oracle" not in text.replace("no oracle", ""), path
+            assert "/root/reference" not in text, path
+
+
+def test_signature_matches_reference(pkg):
+    import inspect
+
+    sig = inspect.signature(pkg.monotonic_align.maximum_path)
+    names = [n for n, p in sig.parameters.items() if p.kind is p.POSITIONAL_OR_KEYWORD]
+    assert names == ["value", "mask"]      # monotonic_align/__init__.py:6
+
+
+def test_contiguous_shard(pkg):
+    from glow_tts_train_b200 import sharding
+
+    for B in (0, 1, 7, 32, 256):
+        for ws in (1, 2, 3, 4, 8):
+            got = [i for r in range(ws) for i in sharding.contiguous_shard(B, ws, r)]
+            assert got == list(range(B))
+            sizes = [len(sharding.contiguous_shard(B, ws, r)) for r in range(ws)]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.contiguous_shard(4, 2, 2)
+
+
+def test_balanced_shards(pkg):
+    from glow_tts_train_b200 import sharding
+
+    rng = np.random.default_rng(0)
+    costs = np.sort(rng.integers(1000, 200000, 64))[::-1]
+    shards = sharding.balanced_shards(costs.tolist(), 8)
+    assert sorted(i for s in shards for i in s) == list(range(64))
+    loads = [sum(costs[i] for i in s) for s in shards]
+    contiguous = [sum(costs[i] for i in sharding.contiguous_shard(64, 8, r)) for r in range(8)]
+    assert max(loads) / min(loads) < 1.1 < max(contiguous) / min(contiguous)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world_size, port, out_dir):
+    sys.path.insert(0, str(REPO))
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    oracle = entry.load_oracle()
+    pkg = entry.load_package()
+    from glow_tts_train_b200 import sharding
+
+    rng = np.random.default_rng(99)                       # same batch on every rank
+    B, T_x, T_y = 7, 12, 40
+    value = (10 * rng.standard_normal((B, T_x, T_y)) - 100).astype(np.float32)
+    t_x = rng.integers(1, T_x + 1, B).astype(np.int32)
+    t_y = np.array([rng.integers(t, T_y + 1) for t in t_x], np.int32)
+    mine = sharding.contiguous_shard(B, world_size, rank)
+    # the shard is processed with NO data-path collective; the CPU oracle stands in for the kernel here
+    local = oracle.maximum_path(value[mine.start:mine.stop], t_x[mine.start:mine.stop], t_y[mine.start:mine.stop])
+    # bench-style reduction: units processed are summed, time is the max over ranks
+    cells = torch.tensor([local.size], dtype=torch.float64)
+    elapsed = torch.tensor([0.001 * (rank + 1)], dtype=torch.float64)
+    dist.all_reduce(cells, op=dist.ReduceOp.SUM)
+    dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    gathered = [None] * world_size
+    dist.all_gather_object(gathered, (mine.start, local))
+    if rank == 0:
+        full = np.concatenate([g[1] for g in sorted(gathered, key=lambda g: g[0])])
+        want = oracle.maximum_path(value, t_x, t_y)
+        np.save(Path(out_dir) / "ok.npy", np.array([np.array_equal(full, want), cells.item() == value.size,
+                                                     abs(elapsed.item() - 0.001 * world_size) < 1e-12]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_equals_single_gloo(tmp_path, oracle, pkg):
+    """world_size 2 on CPU (gloo): the concatenation of per-rank results equals the single-process
+    result, cells are summed and time is max-reduced -- the N>1 contract of bench.py."""
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ok = np.load(tmp_path / "ok.npy")
+    assert ok.all()
