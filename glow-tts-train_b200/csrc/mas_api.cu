@@ -15,6 +15,11 @@ using namespace mas;
 
 namespace {
 
+size_t path_workspace_bytes(int B, int T_x, int T_y) {
+    const size_t a = path_simple_workspace_bytes(B, T_x, T_y), b = path_systolic_workspace_bytes(B, T_x, T_y);
+    return a > b ? a : b;
+}
+
 struct FusedWorkspace {
     size_t logp_bytes, path_ws_bytes;
 };
@@ -22,7 +27,7 @@ struct FusedWorkspace {
 FusedWorkspace fused_ws(int B, int T_x, int T_y) {
     FusedWorkspace w;
     w.logp_bytes = align_up((size_t)B * T_x * T_y * sizeof(float), 256);
-    w.path_ws_bytes = path_simple_workspace_bytes(B, T_x, T_y);
+    w.path_ws_bytes = path_workspace_bytes(B, T_x, T_y);
     return w;
 }
 
@@ -61,7 +66,7 @@ int mas_b200_device_ok(void) {
 
 size_t mas_b200_workspace_bytes(int B, int T_x, int T_y) {
     if (!shape_ok(B, T_x, T_y)) return 0;
-    return path_simple_workspace_bytes(B, T_x, T_y);
+    return path_workspace_bytes(B, T_x, T_y);
 }
 
 size_t mas_b200_fused_workspace_bytes(int B, int D, int T_x, int T_y) {
@@ -101,6 +106,9 @@ int mas_b200_maximum_path_f32(const float *value, int64_t value_stride_b, int64_
     p.T_x = T_x;
     p.T_y = T_y;
     p.max_neg_val = max_neg_val;
+    // the TMA-staged systolic kernel when shape/alignment allow, else the generic kernel
+    int rc = launch_path_systolic(p, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    if (rc != MAS_ERR_UNSUPPORTED_SHAPE) return rc;
     return launch_path_simple(p, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

@@ -31,6 +31,10 @@ struct LogpParams {
 size_t path_simple_workspace_bytes(int B, int T_x, int T_y);
 int launch_path_simple(PathParams p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 
+size_t path_systolic_workspace_bytes(int B, int T_x, int T_y);
+// MAS_ERR_UNSUPPORTED_SHAPE = "not for the TMA path": the caller falls back to launch_path_simple.
+int launch_path_systolic(PathParams p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
 int launch_logp(const LogpParams &p, cudaStream_t stream);
 
 }  // namespace mas

@@ -28,7 +28,7 @@ def run_gpu(pkg, value, t_x, t_y, via_mask=True, **kw):
 
 
 def as_i32(t):
-    return t.cpu().numpy().astype(np.int32)
+    return t.float().cpu().numpy().astype(np.int32)
 
 
 def test_golden_kat(pkg, mas_kat):
