@@ -9,6 +9,7 @@
 
 namespace mas {
 thread_local int g_last_cuda_error = 0;
+long long *g_dbg_cycles = nullptr;
 }
 
 using namespace mas;
@@ -55,6 +56,8 @@ const char *mas_b200_status_string(int status) {
 }
 
 int mas_b200_last_cuda_error(void) { return g_last_cuda_error; }
+
+void mas_b200_debug_set_cycle_buffer(void *device_buffer) { g_dbg_cycles = static_cast<long long *>(device_buffer); }
 
 int mas_b200_device_ok(void) {
     int dev = 0, major = 0;
@@ -106,6 +109,7 @@ int mas_b200_maximum_path_f32(const float *value, int64_t value_stride_b, int64_
     p.T_x = T_x;
     p.T_y = T_y;
     p.max_neg_val = max_neg_val;
+    p.dbg_cycles = g_dbg_cycles;
     // the TMA-staged systolic kernel when shape/alignment allow, else the generic kernel
     int rc = launch_path_systolic(p, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if (rc != MAS_ERR_UNSUPPORTED_SHAPE) return rc;

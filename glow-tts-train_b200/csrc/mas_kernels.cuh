@@ -19,6 +19,7 @@ struct PathParams {
     int32_t *ws_tok;       // workspace: frame -> token [B][T_y] when frame_token is null
     int B, T_x, T_y;
     float max_neg_val;
+    long long *dbg_cycles;  // profiling hook (mas_b200_debug_set_cycle_buffer): [B][16 warps][16] clock64 stamps, or null
 };
 
 // Log-likelihood matrix arguments (mas_b200_logp_f32).
@@ -34,6 +35,9 @@ int launch_path_simple(PathParams p, void *workspace, size_t workspace_bytes, cu
 size_t path_systolic_workspace_bytes(int B, int T_x, int T_y);
 // MAS_ERR_UNSUPPORTED_SHAPE = "not for the TMA path": the caller falls back to launch_path_simple.
 int launch_path_systolic(PathParams p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// developer profiling hook: when non-null, kernels stamp clock64() phase times into it
+extern long long *g_dbg_cycles;
 
 int launch_logp(const LogpParams &p, cudaStream_t stream);
 

@@ -80,18 +80,25 @@ __device__ __forceinline__ void cell(float &stay, float adv, float l, uint32_t &
 }
 
 // 32 frames of R tokens per lane.  tile: this warp's [32R][32] fp32 box (128B-swizzled).
+// The loop over 4-frame groups is deliberately NOT unrolled: a DP warp runs alone on its scheduler,
+// so nothing hides instruction fetch and the body has to stay inside the L0 instruction cache.
 template <int R, bool kGuard>
 __device__ __forceinline__ void sweep_block(const float *__restrict__ tile, float (&v)[R], uint32_t (&acc)[R],
                                             float &carry, const float4 *__restrict__ bnd_in, float4 *bnd_out,
                                             bool first_block_of_warp0, int lane, int row0, int col0, float neg) {
+    int swz[R];                                     // per-row XOR term of the 128B swizzle
+    const float *rowp[R];
 #pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int q = lane * R + i;
+        rowp[i] = tile + q * kBlk;
+        swz[i] = q & 7;
+    }
+#pragma unroll 1
     for (int g = 0; g < 8; ++g) {
         float4 L[R];
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-            const int q = lane * R + i;
-            L[i] = *reinterpret_cast<const float4 *>(tile + q * kBlk + ((g ^ (q & 7)) << 2));
-        }
+        for (int i = 0; i < R; ++i) L[i] = *reinterpret_cast<const float4 *>(rowp[i] + ((g ^ swz[i]) << 2));
         // scores of the previous warp's last token after frames col0+4g-1 .. col0+4g+2
         float up4[4];
         if (bnd_in != nullptr) {
@@ -107,9 +114,11 @@ __device__ __forceinline__ void sweep_block(const float *__restrict__ tile, floa
             up4[1] = up4[2] = up4[3] = neg;
         }
         float out4[4];
+        uint32_t acc4[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) acc4[i] = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int bit = 4 * g + j;
             float up = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
             if (lane == 0) up = up4[j];
 #pragma unroll
@@ -118,12 +127,14 @@ __device__ __forceinline__ void sweep_block(const float *__restrict__ tile, floa
                 if (kGuard) {
                     // below the diagonal (token > frame) the reference never computes the cell and
                     // reads -1e9 instead (core.pyx:19-20): adding 0 keeps the score at exactly -1e9
-                    if (row0 + i > col0 + bit) l = 0.f;
+                    if (row0 + i > col0 + 4 * g + j) l = 0.f;
                 }
-                cell(v[i], (i == 0) ? up : v[i - 1], l, acc[i], bit);
+                cell(v[i], (i == 0) ? up : v[i - 1], l, acc4[i], j);
             }
             out4[j] = v[R - 1];
         }
+#pragma unroll
+        for (int i = 0; i < R; ++i) acc[i] |= acc4[i] << (4 * g);
         if (bnd_out != nullptr && lane == 31) bnd_out[g] = make_float4(out4[0], out4[1], out4[2], out4[3]);
     }
 }
@@ -140,8 +151,9 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
     const int T_x = p.T_x, T_y = p.T_y;
 
     float *ring = reinterpret_cast<float *>(smem + plan.off_ring);
-    uint32_t *bits = plan.bits_in_smem ? reinterpret_cast<uint32_t *>(smem + plan.off_bits)
-                                       : p.ws_bits + (size_t)b * plan.nblk * plan.rows;   // [nblk][rows]
+    // packed directions [nblk][rows]: shared memory when they fit, else the caller's workspace
+    uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem + plan.off_bits);
+    uint32_t *bits_g = plan.bits_in_smem ? nullptr : p.ws_bits + (size_t)b * plan.nblk * plan.rows;
     float *bnd = reinterpret_cast<float *>(smem + plan.off_bnd);                          // [W][kBndBlocks*32]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + plan.off_bar);                   // [W][S]
     int *done = reinterpret_cast<int *>(smem + plan.off_done);                            // [W+1]
@@ -198,6 +210,9 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
     if (dp_warp && lane == 0) done[warp] = active ? cb0 - 1 : kDoneAll;
     __syncthreads();
 
+    long long *dbg = p.dbg_cycles ? p.dbg_cycles + ((size_t)b * 16 + warp) * 16 : nullptr;
+    long long t_wait_prev = 0, t_wait_next = 0, t_wait_tma = 0, t_sweep = 0, t_tail = 0;
+    if (dbg && lane == 0) dbg[0] = clock64();
     if (dp_warp) {
         if (active) {
             float *my_ring = ring + (size_t)warp * S * (rows_per_warp * kBlk);
@@ -223,17 +238,27 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
                 const int k = cb - cb0, slot = k % S;
                 const uint32_t parity = (k / S) & 1;
                 uint32_t spins = 0;
+                long long t0 = dbg ? clock64() : 0;
                 if (warp > 0)                                   // previous warp has published block cb
                     while (ptx::ld_acquire_shared(&done[warp - 1]) <= cb)
                         if (++spins > kSpinLimit) spin_fail();
+                long long t1 = dbg ? clock64() : 0;
                 if (bnd_out_base != nullptr)                    // next warp has consumed block cb - ring depth
                     while (ptx::ld_acquire_shared(&done[warp + 1]) + kBndBlocks <= cb)
                         if (++spins > kSpinLimit) spin_fail();
+                long long t2 = dbg ? clock64() : 0;
                 while (!ptx::mbar_try_wait(&my_full[slot], parity))
                     if (++spins > kSpinLimit) spin_fail();
+                if (dbg) {
+                    const long long t3 = clock64();
+                    t_wait_prev += t1 - t0;
+                    t_wait_next += t2 - t1;
+                    t_wait_tma += t3 - t2;
+                }
                 if (cb == cb0 && warp > 0)                      // score of token x0-1 on the diagonal frame x0-1
                     carry = bnd_in_base[((cb0 - 1) % kBndBlocks) * kBlk + (kBlk - 1)];
 
+                const long long t4 = dbg ? clock64() : 0;
 #pragma unroll
                 for (int i = 0; i < R; ++i) acc[i] = 0u;
                 const float *tile = my_ring + (size_t)slot * rows_per_warp * kBlk;
@@ -243,8 +268,14 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
                     sweep_block<R, true>(tile, v, acc, carry, bin, bout, warp == 0 && cb == 0, lane, row0, cb * kBlk, p.max_neg_val);
                 else
                     sweep_block<R, false>(tile, v, acc, carry, bin, bout, false, lane, row0, cb * kBlk, p.max_neg_val);
+                const long long t5 = dbg ? clock64() : 0;
+                if (plan.bits_in_smem) {
 #pragma unroll
-                for (int i = 0; i < R; ++i) bits[(size_t)cb * plan.rows + row0 + i] = acc[i];
+                    for (int i = 0; i < R; ++i) bits_s[cb * plan.rows + row0 + i] = acc[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) bits_g[(size_t)cb * plan.rows + row0 + i] = acc[i];
+                }
                 __syncwarp();
                 if (lane == 0) {
                     if (cb + S <= cbend) {
@@ -253,9 +284,22 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
                     }
                     ptx::st_release_shared(&done[warp], cb + 1);
                 }
+                if (dbg) {
+                    t_sweep += t5 - t4;
+                    t_tail += clock64() - t5;
+                }
             }
             __syncwarp();
             if (lane == 0) ptx::st_release_shared(&done[warp], kDoneAll);
+        }
+        if (dbg && lane == 0) {
+            dbg[1] = clock64();
+            dbg[2] = t_wait_prev;
+            dbg[3] = t_wait_next;
+            dbg[4] = t_wait_tma;
+            dbg[8] = t_sweep;
+            dbg[9] = t_tail;
+            dbg[10] = cbend - cb0 + 1;
         }
     } else {
         // ---- filler warp: zero the dense output while the sweep runs ----
@@ -270,31 +314,44 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
             ptx::st_global_cs_v4(o4 + i + 96, z4);
         }
         for (; i < n4; i += 32) ptx::st_global_cs_v4(o4 + i, z4);
+        if (dbg && lane == 0) dbg[1] = clock64();
     }
     if (!plan.bits_in_smem) __threadfence_block();
     __syncthreads();
 
-    // ---- backtrack (core.pyx:32-35) by tokens: where did the path enter token x? ----
-    if (tid == 0 && tx > 0) {
-        int x = tx - 1, y = ty - 1;
+    // ---- backtrack (core.pyx:32-35) by TOKENS, warp 0 in lockstep ----
+    // State: the path sits on token x for frames (.., y_hi]; ys <= y_hi is how far left that run has
+    // been scanned without finding the frame where the path stepped onto x.  Lane k holds the
+    // direction word of token x-k for the current 32-frame block, so a block is fetched with one
+    // load and every further token costs a shuffle + count-leading-zeros instead of a memory trip.
+    // Stepping is forced on the diagonal (frame == token, core.pyx:34 `index == y`).
+    if (dbg && tid == 0) dbg[5] = clock64();
+    if (warp == 0 && tx > 0) {
+        int x = tx - 1, y_hi = ty - 1, ys = ty - 1;
         while (x > 0) {
-            int cb = y >> 5;
-            const int cb_diag = x >> 5;                          // block holding frame == x (forced step, core.pyx:34)
-            const uint32_t *col = bits + x;
-            uint32_t w = (plan.bits_in_smem ? col[(size_t)cb * plan.rows] : __ldcg(col + (size_t)cb * plan.rows)) &
-                         (0xffffffffu >> (31 - (y & 31)));
-            while (w == 0u && cb > cb_diag) {
-                --cb;
-                w = plan.bits_in_smem ? col[(size_t)cb * plan.rows] : __ldcg(col + (size_t)cb * plan.rows);
+            const int cb = ys >> 5;
+            const int r = x - lane;
+            uint32_t wd = 0u;
+            if (r > 0) wd = plan.bits_in_smem ? bits_s[cb * plan.rows + r] : __ldcg(bits_g + (size_t)cb * plan.rows + r);
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                const uint32_t w = __shfl_sync(0xffffffffu, wd, k);
+                const uint32_t m = w & (0xffffffffu >> (31 - (ys & 31)));
+                int ylo = (m != 0u) ? (cb << 5) + 31 - __clz(m) : -1;
+                ylo = max(ylo, x);
+                if (ylo < (cb << 5)) {          // stepped onto x in an earlier block: same token, next block
+                    ys = (cb << 5) - 1;
+                    break;
+                }
+                if (lane == 0) run[x] = make_int2(ylo, y_hi);
+                y_hi = ys = ylo - 1;
+                --x;
+                if (x == 0 || (ys >> 5) != cb) break;
             }
-            int ylo = (w != 0u) ? (cb << 5) + 31 - __clz(w) : -1;
-            ylo = max(ylo, x);
-            run[x] = make_int2(ylo, y);
-            y = ylo - 1;
-            --x;
         }
-        run[0] = make_int2(0, y);
+        if (lane == 0) run[0] = make_int2(0, y_hi);
     }
+    if (dbg && tid == 0) dbg[6] = clock64();
     __syncthreads();
 
     // ---- dense path: ones, durations, frame -> token ----
@@ -313,6 +370,7 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
     }
     if (p.frame_token)
         for (int y = ty + tid; y < T_y; y += blockDim.x) p.frame_token[(int64_t)b * T_y + y] = -1;
+    if (dbg && lane == 0) dbg[7] = clock64();
 }
 
 // ---------------------------------------------------------------------------------------------

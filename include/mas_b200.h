@@ -54,6 +54,9 @@ int mas_b200_abi_version(void);
 const char *mas_b200_status_string(int status);
 /* cudaError_t of the last failing CUDA call made by this library on the calling thread (0 if none) */
 int mas_b200_last_cuda_error(void);
+/* Developer profiling hook: when `device_buffer` (int64 [B][16][16], device memory) is non-NULL the
+ * kernels stamp clock64() phase boundaries per warp into it; NULL (the default) switches it off. */
+void mas_b200_debug_set_cycle_buffer(void *device_buffer);
 /* MAS_OK iff the current CUDA device can run the kernels (compute capability 10.x). */
 int mas_b200_device_ok(void);
 
