@@ -11,11 +11,19 @@
 // frames] boxes (128-byte rows, SWIZZLE_128B so that the per-thread 16-byte row reads are
 // bank-conflict free), refilled by the warp's lane 0 as soon as a box has been consumed.
 //
-// Backtrack directions are packed 1 bit per cell (32 frames of one token per word) into shared
-// memory, or into the caller's workspace when they do not fit.  The backtrack of core.pyx:32-35
-// then walks TOKENS, not frames: for token x it finds, with one count-leading-zeros, the frame at
-// which the path entered x.  A dedicated warp zero-fills the dense output while the sweep runs;
-// the ones are written last.
+// Per cell the sweep issues four instructions: FMNMX.NAN (best predecessor), FADD (new score),
+// FADD (stay - advance, whose SIGN is the backtrack direction: advance > stay <=> stay - advance < 0,
+// exact in IEEE arithmetic without flush-to-zero) and one funnel shift that pushes that sign bit
+// into the token's direction word.  This equals the reference's compare/select bit for bit as long
+// as every score is finite; a non-finite score is sticky under max.NaN, so it is detected once per
+// token at the end of the sweep and the (rare) utterance is redone by an exact compare/select
+// sweep inside the same kernel.
+//
+// Directions are packed 1 bit per cell (32 frames of one token per word) into shared memory, or
+// into the caller's workspace when they do not fit.  The backtrack of core.pyx:32-35 walks TOKENS,
+// not frames: for token x it finds, with one count-leading-zeros, the frame at which the path
+// stepped onto x.  A dedicated warp zero-fills the dense output while the sweep runs; the ones are
+// written last.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -29,6 +37,7 @@ constexpr int kBlk = 32;            // frames per box / per direction word
 constexpr int kMaxDpWarps = 15;     // + 1 filler warp = 512 threads
 constexpr int kBndBlocks = 4;       // depth of the warp-to-warp boundary ring, in 32-frame blocks
 constexpr int kDoneAll = 0x3fffffff;
+constexpr int kZeroBytes = 16384;  // shared zero page the filler streams to the dense output with bulk copies
 constexpr uint32_t kSpinLimit = 1u << 27;   // watchdog: a wedged wait traps instead of hanging the GPU
 
 struct Plan {
@@ -37,7 +46,7 @@ struct Plan {
     int nblk;            // ceil(T_y / 32)
     int bits_in_smem;
     // byte offsets into dynamic shared memory (base is 1024-aligned)
-    int off_ring, off_bits, off_bnd, off_bar, off_done, off_run, total;
+    int off_ring, off_bits, off_bnd, off_bar, off_done, off_run, off_zero, total;
 };
 
 __host__ __device__ inline int stage_bytes(int R) { return kBlk * R * kBlk * 4; }   // 32R rows x 128 B
@@ -53,11 +62,13 @@ __host__ __device__ inline Plan make_plan(int R, int W, int S, int T_y, bool bit
     int off = 0;
     p.off_ring = off;
     off += W * S * stage_bytes(R);
-    p.off_run = p.off_ring;                       // run table aliases the ring (free after the sweep)
+    p.off_run = p.off_ring;                       // run table / exact-sweep columns alias the ring (free after the sweep)
     p.off_bits = off;
     if (bits_in_smem) off += p.nblk * p.rows * 4;
+    p.off_zero = off;
+    off += kZeroBytes;
     p.off_bnd = off;
-    off += W * kBndBlocks * kBlk * 4;
+    off += (W + 1) * kBndBlocks * kBlk * 4;       // ring w = boundary INTO warp w; ring 0 is constant -1e9
     p.off_bar = off;
     off += W * S * 8;
     p.off_done = off;
@@ -66,26 +77,83 @@ __host__ __device__ inline Plan make_plan(int R, int W, int S, int T_y, bool bit
     return p;
 }
 
-__device__ __forceinline__ void spin_fail() {
-    __trap();
+__device__ __forceinline__ void spin_fail() { __trap(); }
+
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
 }
 
-// One (token, frame) cell: core.pyx:19-30.  `adv` = score of token-1 at frame-1, `stay` = score of
-// this token at frame-1.  Strict '>' so that a tie (or a NaN) keeps `stay`, like core.c:2697-2708.
-__device__ __forceinline__ void cell(float &stay, float adv, float l, uint32_t &acc, int bit) {
-    const bool take = adv > stay;
-    const float best = take ? adv : stay;
-    stay = best + l;                       // plain fp32 round-to-nearest add (core.pyx:30)
-    acc |= take ? (1u << bit) : 0u;
+// One (token, frame) cell of core.pyx:19-30.  `adv` = score of token-1 at frame-1, `stay` = score of
+// this token at frame-1.  The direction bit (advance strictly better, core.c:2697-2708) is the sign
+// of stay - adv; it is shifted into `acc` from the right, so after 32 frames bit 31 is the block's
+// first frame (the caller bit-reverses the word).
+__device__ __forceinline__ void cell_fast(float &stay, float adv, float l, uint32_t &acc) {
+    const float diff = stay - adv;
+    const float best = fmax_nan(adv, stay);
+    stay = best + l;                                       // plain fp32 round-to-nearest add (core.pyx:30)
+    acc = __funnelshift_l(__float_as_uint(diff), acc, 1);
 }
 
-// 32 frames of R tokens per lane.  tile: this warp's [32R][32] fp32 box (128B-swizzled).
-// The loop over 4-frame groups is deliberately NOT unrolled: a DP warp runs alone on its scheduler,
-// so nothing hides instruction fetch and the body has to stay inside the L0 instruction cache.
-template <int R, bool kGuard>
+// Four frames (one 16-byte group) of R tokens per lane.
+template <int R>
+__device__ __forceinline__ void sweep_group(const float4 (&L)[R], const float4 &b, float (&v)[R], uint32_t (&acc)[R],
+                                            float &carry, float4 *bnd_out, int g, int lane) {
+    // scores of the previous warp's last token after frames col0+4g-1 .. col0+4g+2
+    const float up4[4] = {carry, b.x, b.y, b.z};
+    carry = b.w;
+    float out4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float up = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
+        if (lane == 0) up = up4[j];
+#pragma unroll
+        for (int i = R - 1; i >= 0; --i) {
+            const float l = (j == 0) ? L[i].x : (j == 1) ? L[i].y : (j == 2) ? L[i].z : L[i].w;
+            cell_fast(v[i], (i == 0) ? up : v[i - 1], l, acc[i]);
+        }
+        out4[j] = v[R - 1];
+    }
+    if (bnd_out != nullptr && lane == 31) bnd_out[g] = make_float4(out4[0], out4[1], out4[2], out4[3]);
+}
+
+// Below the diagonal (token > frame) the reference never computes a cell and reads -1e9 in its place
+// (core.pyx:18-20).  Zeroing those scores in the staged box makes the sweep reproduce that without
+// a per-cell test: max(-1e9, -1e9) + 0 stays exactly -1e9.  Only the first R blocks of a warp touch
+// the diagonal.  Each lane edits its own rows (in place, swizzled 16-byte chunks).
+template <int R>
+__device__ __forceinline__ void zero_below_diagonal(float *tile, int lane, int row0, int col0) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int q = lane * R + i;
+        const int d = row0 + i - col0;              // frames [0, d) of this block are below the diagonal
+        if (d <= 0) continue;
+        float *rowp = tile + q * kBlk;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (4 * c >= d) break;
+            float4 *p4 = reinterpret_cast<float4 *>(rowp + ((c ^ (q & 7)) << 2));
+            float4 x = *p4;
+            x.x = 0.f;
+            if (4 * c + 1 < d) x.y = 0.f;
+            if (4 * c + 2 < d) x.z = 0.f;
+            if (4 * c + 3 < d) x.w = 0.f;
+            *p4 = x;
+        }
+    }
+}
+
+// 32 frames of R tokens per lane.  tile: this warp's [32R][32] fp32 box (128B-swizzled); bnd_in: the
+// previous warp's last-token scores for these 32 frames (for warp 0 a constant -1e9 ring: token 0
+// can only be "advanced into" from outside the lattice, core.pyx:23-27).
+// The loop is software-pipelined by hand (group g+1 is fetched from shared memory while group g is
+// swept) and only unrolled twice: a DP warp runs alone on its scheduler, so nothing else hides a
+// shared-memory round trip or an instruction-cache miss.
+template <int R>
 __device__ __forceinline__ void sweep_block(const float *__restrict__ tile, float (&v)[R], uint32_t (&acc)[R],
                                             float &carry, const float4 *__restrict__ bnd_in, float4 *bnd_out,
-                                            bool first_block_of_warp0, int lane, int row0, int col0, float neg) {
+                                            int lane) {
     int swz[R];                                     // per-row XOR term of the 128B swizzle
     const float *rowp[R];
 #pragma unroll
@@ -94,67 +162,107 @@ __device__ __forceinline__ void sweep_block(const float *__restrict__ tile, floa
         rowp[i] = tile + q * kBlk;
         swz[i] = q & 7;
     }
+    float4 LA[R], LB[R], bA, bB;
+#pragma unroll
+    for (int i = 0; i < R; ++i) LA[i] = *reinterpret_cast<const float4 *>(rowp[i] + (swz[i] << 2));
+    bA = bnd_in[0];
 #pragma unroll 1
-    for (int g = 0; g < 8; ++g) {
-        float4 L[R];
+    for (int g = 0; g < 8; g += 2) {
 #pragma unroll
-        for (int i = 0; i < R; ++i) L[i] = *reinterpret_cast<const float4 *>(rowp[i] + ((g ^ swz[i]) << 2));
-        // scores of the previous warp's last token after frames col0+4g-1 .. col0+4g+2
-        float up4[4];
-        if (bnd_in != nullptr) {
-            const float4 b = bnd_in[g];
-            up4[0] = carry;
-            up4[1] = b.x;
-            up4[2] = b.y;
-            up4[3] = b.z;
-            carry = b.w;
-        } else {
-            // token 0: "advance" comes from outside the lattice: 0 at frame 0, -1e9 after (core.pyx:23-27)
-            up4[0] = (first_block_of_warp0 && g == 0) ? 0.f : neg;
-            up4[1] = up4[2] = up4[3] = neg;
-        }
-        float out4[4];
-        uint32_t acc4[R];
+        for (int i = 0; i < R; ++i) LB[i] = *reinterpret_cast<const float4 *>(rowp[i] + (((g + 1) ^ swz[i]) << 2));
+        bB = bnd_in[g + 1];
+        sweep_group<R>(LA, bA, v, acc, carry, bnd_out, g, lane);
+        const int gn = (g + 2) & 7;                 // the last prefetch wraps to group 0 and is discarded
 #pragma unroll
-        for (int i = 0; i < R; ++i) acc4[i] = 0u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float up = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
-            if (lane == 0) up = up4[j];
-#pragma unroll
-            for (int i = R - 1; i >= 0; --i) {
-                float l = (j == 0) ? L[i].x : (j == 1) ? L[i].y : (j == 2) ? L[i].z : L[i].w;
-                if (kGuard) {
-                    // below the diagonal (token > frame) the reference never computes the cell and
-                    // reads -1e9 instead (core.pyx:19-20): adding 0 keeps the score at exactly -1e9
-                    if (row0 + i > col0 + 4 * g + j) l = 0.f;
-                }
-                cell(v[i], (i == 0) ? up : v[i - 1], l, acc4[i], j);
-            }
-            out4[j] = v[R - 1];
-        }
-#pragma unroll
-        for (int i = 0; i < R; ++i) acc[i] |= acc4[i] << (4 * g);
-        if (bnd_out != nullptr && lane == 31) bnd_out[g] = make_float4(out4[0], out4[1], out4[2], out4[3]);
+        for (int i = 0; i < R; ++i) LA[i] = *reinterpret_cast<const float4 *>(rowp[i] + ((gn ^ swz[i]) << 2));
+        bA = bnd_in[gn];
+        sweep_group<R>(LB, bB, v, acc, carry, bnd_out, g + 1, lane);
     }
 }
 
-template <int R>
-__global__ void __launch_bounds__((kMaxDpWarps + 1) * 32, 1)
+// Exact compare/select sweep for utterances whose scores are not all finite (NaN / +-inf): the
+// whole CTA walks the frames with a barrier per frame, score column in shared memory, scores read
+// straight from global memory.  Slow, rare, and literal: core.pyx:17-30 as written.
+// col: [2][rows] floats.  Writes the same [nblk][rows] direction words as the fast sweep.
+template <bool kSmemBits>
+__device__ void exact_sweep_cta(const float *__restrict__ val, int64_t stride_x, float *col, uint32_t *bits, int rows,
+                                int tx, int ty, float neg) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int x = tid; x < tx; x += nthr) col[x] = neg;
+    __syncthreads();
+    int buf = 0;
+    for (int y = 0; y < ty; ++y) {
+        const float *vin = col + buf * rows;
+        float *vout = col + (buf ^ 1) * rows;
+        for (int x = tid; x < tx; x += nthr) {
+            const float stay = vin[x];                                      // == -1e9 while x > y-1, core.pyx:19-20
+            const float adv = (x == 0) ? ((y == 0) ? 0.f : neg) : vin[x - 1];   // core.pyx:23-29
+            const float l = (x > y) ? 0.f : __ldg(val + (int64_t)x * stride_x + y);
+            const bool take = adv > stay;
+            vout[x] = (take ? adv : stay) + l;
+            const uint32_t bit = ((take || (x == y && x > 0)) ? 1u : 0u) << (y & 31);
+            uint32_t *w = bits + (size_t)(y >> 5) * rows + x;
+            if (kSmemBits)
+                *w = ((y & 31) ? *w : 0u) | bit;
+            else
+                __stcg(w, ((y & 31) ? __ldcg(w) : 0u) | bit);
+        }
+        buf ^= 1;
+        __syncthreads();
+    }
+}
+
+// Backtrack of core.pyx:32-35, walking TOKENS instead of frames.  The path sits on token x for
+// frames (.., y_hi]; the frame where it stepped onto x is the highest set direction bit at or
+// below the scan position -- one count-leading-zeros per token.  The forced step on the diagonal
+// (frame == token, core.pyx:34 `index == y`) was OR-ed into the words by the sweep.
+// bits: [nblk][rows] words, bit j of word (cb, x) = direction of cell (x, 32 cb + j).
+template <bool kSmem>
+__device__ __forceinline__ void backtrack_tokens(const uint32_t *bits, int rows, int tx, int ty, int2 *run) {
+    int x = tx - 1, y_hi = ty - 1;
+    int base = y_hi & ~31;
+    uint32_t elig = 0xffffffffu >> (31 - (y_hi & 31));     // bits at or below the scan position
+    const uint32_t *p = bits + (size_t)(y_hi >> 5) * rows + x;
+    // Branches are what a lone thread pays for (~25 cycles each): one per token, two per block.
+    while (x > 0) {
+        uint32_t m = (kSmem ? *p : __ldcg(p)) & elig;
+        while (m != 0u) {                                   // the path stepped onto x inside this block
+            const uint32_t wn = kSmem ? p[-1] : __ldcg(p - 1);   // next token, same block
+            const int lo = 31 - __clz(m);
+            run[x] = make_int2(base + lo, y_hi);
+            y_hi = base + lo - 1;
+            --x;
+            --p;
+            elig = (1u << lo) - 1u;                         // lo == 0: nothing left here, leave the block
+            m = (x > 0) ? (wn & elig) : 0u;
+        }
+        base -= 32;                                         // same token, previous block
+        p -= rows;
+        elig = 0xffffffffu;
+    }
+    run[0] = make_int2(0, y_hi);
+}
+
+// kThreads: launch bound.  Up to 4 sweep warps (+ the filler) run as 160 threads so that the
+// compiler may keep every loop-invariant in registers (a 512-thread bound caps it at 128 and it
+// starts re-reading kernel parameters from the constant bank inside the block loop).
+template <int R, int kThreads, bool kDbg>
+__global__ void __launch_bounds__(kThreads, 1)
 mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p, Plan plan) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ float s_len[2];
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int W = plan.W, S = plan.S;
+    const int W = plan.W, S = plan.S, rows = plan.rows;
     const int T_x = p.T_x, T_y = p.T_y;
+    const bool bits_smem = plan.bits_in_smem != 0;
 
     float *ring = reinterpret_cast<float *>(smem + plan.off_ring);
     // packed directions [nblk][rows]: shared memory when they fit, else the caller's workspace
     uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem + plan.off_bits);
-    uint32_t *bits_g = plan.bits_in_smem ? nullptr : p.ws_bits + (size_t)b * plan.nblk * plan.rows;
-    float *bnd = reinterpret_cast<float *>(smem + plan.off_bnd);                          // [W][kBndBlocks*32]
+    uint32_t *bits_g = bits_smem ? nullptr : p.ws_bits + (size_t)b * plan.nblk * rows;
+    float *bnd = reinterpret_cast<float *>(smem + plan.off_bnd);                          // [W+1][kBndBlocks*32]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + plan.off_bar);                   // [W][S]
     int *done = reinterpret_cast<int *>(smem + plan.off_done);                            // [W+1]
     int2 *run = reinterpret_cast<int2 *>(smem + plan.off_run);                            // [T_x] after the sweep
@@ -188,7 +296,7 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
     const int tx = len.tx, ty = len.ty;
 
     // ---- per-warp geometry: tokens [x0, x0+32R), 32-frame blocks [cb0, cbend] ----
-    const int rows_per_warp = kBlk * R;
+    constexpr int rows_per_warp = kBlk * R;
     const int x0 = warp * rows_per_warp;
     const bool dp_warp = warp < W;
     const bool active = dp_warp && x0 < tx;
@@ -204,20 +312,23 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
         ptx::fence_proxy_async();
         done[W] = kDoneAll;                                  // nobody consumes the last warp's boundary
     }
+    // what "advances" into token 0 after frame 0 (core.pyx:26-27)
+    for (int i = tid; i < kBndBlocks * kBlk; i += blockDim.x) bnd[i] = p.max_neg_val;
     // done[w] = number of 32-frame blocks warp w has finished.  It starts one short of the warp's
     // first block: the warp still needs the LAST frame of block cb0-1 from its predecessor (the
     // diagonal cell of token x0-1), so that ring slot must not be recycled yet.
     if (dp_warp && lane == 0) done[warp] = active ? cb0 - 1 : kDoneAll;
     __syncthreads();
 
-    long long *dbg = p.dbg_cycles ? p.dbg_cycles + ((size_t)b * 16 + warp) * 16 : nullptr;
-    long long t_wait_prev = 0, t_wait_next = 0, t_wait_tma = 0, t_sweep = 0, t_tail = 0;
-    if (dbg && lane == 0) dbg[0] = clock64();
+    long long *dbg = (kDbg && p.dbg_cycles) ? p.dbg_cycles + ((size_t)b * 16 + warp) * 16 : nullptr;
+    long long t_wait_prev = 0, t_wait_next = 0, t_wait_tma = 0, t_sweep = 0;
+    if (kDbg && dbg && lane == 0) dbg[0] = clock64();
+    int nonfinite = 0;
     if (dp_warp) {
         if (active) {
             float *my_ring = ring + (size_t)warp * S * (rows_per_warp * kBlk);
             uint64_t *my_full = full + warp * S;
-            const uint32_t box_bytes = stage_bytes(R);
+            constexpr uint32_t box_bytes = kBlk * R * kBlk * 4;
             if (lane == 0) {
                 ptx::prefetch_tensormap(&tmap);
                 for (int k = 0; k < S && cb0 + k <= cbend; ++k) {
@@ -229,129 +340,142 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
             uint32_t acc[R];
 #pragma unroll
             for (int i = 0; i < R; ++i) v[i] = p.max_neg_val;
-            float carry = p.max_neg_val;
-            const float *bnd_in_base = (warp > 0) ? bnd + (size_t)(warp - 1) * kBndBlocks * kBlk : nullptr;
-            float *bnd_out_base = (warp + 1 < W) ? bnd + (size_t)warp * kBndBlocks * kBlk : nullptr;
+            float carry = (warp == 0) ? 0.f : p.max_neg_val;   // frame 0 of token 0 starts from 0 (core.pyx:24-25)
+            const float *bnd_in_base = bnd + (size_t)warp * kBndBlocks * kBlk;
+            float *bnd_out_base = (warp + 1 < W) ? bnd + (size_t)(warp + 1) * kBndBlocks * kBlk : nullptr;
             const int row0 = x0 + lane * R;
+            int slot = 0;
+            uint32_t parity = 0;
+
+            // cached progress of the neighbours: shared memory is only polled when the cached value
+            // does not already answer the question
+            int seen_prev = (warp > 0) ? -1 : kDoneAll;
+            int seen_next = (bnd_out_base != nullptr) ? -1 : kDoneAll;
+            const bool lane0 = lane == 0;
 
             for (int cb = cb0; cb <= cbend; ++cb) {
-                const int k = cb - cb0, slot = k % S;
-                const uint32_t parity = (k / S) & 1;
                 uint32_t spins = 0;
-                long long t0 = dbg ? clock64() : 0;
-                if (warp > 0)                                   // previous warp has published block cb
-                    while (ptx::ld_acquire_shared(&done[warp - 1]) <= cb)
-                        if (++spins > kSpinLimit) spin_fail();
-                long long t1 = dbg ? clock64() : 0;
-                if (bnd_out_base != nullptr)                    // next warp has consumed block cb - ring depth
-                    while (ptx::ld_acquire_shared(&done[warp + 1]) + kBndBlocks <= cb)
-                        if (++spins > kSpinLimit) spin_fail();
-                long long t2 = dbg ? clock64() : 0;
+                const long long t0 = kDbg ? clock64() : 0;
+                while (seen_prev <= cb) {                       // previous warp has published block cb
+                    seen_prev = ptx::ld_acquire_shared(&done[warp - 1]);
+                    if (++spins > kSpinLimit) spin_fail();
+                }
+                while (seen_next + kBndBlocks <= cb) {          // next warp has consumed block cb - ring depth
+                    seen_next = ptx::ld_acquire_shared(&done[warp + 1]);
+                    if (++spins > kSpinLimit) spin_fail();
+                }
+                const long long t2 = kDbg ? clock64() : 0;
                 while (!ptx::mbar_try_wait(&my_full[slot], parity))
                     if (++spins > kSpinLimit) spin_fail();
-                if (dbg) {
-                    const long long t3 = clock64();
-                    t_wait_prev += t1 - t0;
-                    t_wait_next += t2 - t1;
-                    t_wait_tma += t3 - t2;
-                }
+                const long long t3 = kDbg ? clock64() : 0;
                 if (cb == cb0 && warp > 0)                      // score of token x0-1 on the diagonal frame x0-1
-                    carry = bnd_in_base[((cb0 - 1) % kBndBlocks) * kBlk + (kBlk - 1)];
+                    carry = bnd_in_base[((cb0 - 1) & (kBndBlocks - 1)) * kBlk + (kBlk - 1)];
 
-                const long long t4 = dbg ? clock64() : 0;
 #pragma unroll
                 for (int i = 0; i < R; ++i) acc[i] = 0u;
-                const float *tile = my_ring + (size_t)slot * rows_per_warp * kBlk;
-                const float4 *bin = bnd_in_base ? reinterpret_cast<const float4 *>(bnd_in_base + (cb % kBndBlocks) * kBlk) : nullptr;
-                float4 *bout = bnd_out_base ? reinterpret_cast<float4 *>(bnd_out_base + (cb % kBndBlocks) * kBlk) : nullptr;
-                if (cb < cb0 + R)
-                    sweep_block<R, true>(tile, v, acc, carry, bin, bout, warp == 0 && cb == 0, lane, row0, cb * kBlk, p.max_neg_val);
-                else
-                    sweep_block<R, false>(tile, v, acc, carry, bin, bout, false, lane, row0, cb * kBlk, p.max_neg_val);
-                const long long t5 = dbg ? clock64() : 0;
-                if (plan.bits_in_smem) {
+                float *tile = my_ring + (size_t)slot * rows_per_warp * kBlk;
+                const float4 *bin = reinterpret_cast<const float4 *>(bnd_in_base + (cb & (kBndBlocks - 1)) * kBlk);
+                float4 *bout = bnd_out_base ? reinterpret_cast<float4 *>(bnd_out_base + (cb & (kBndBlocks - 1)) * kBlk) : nullptr;
+                const int col0 = cb * kBlk;
+                const bool on_diagonal = cb < cb0 + R;        // warp-uniform
+                if (on_diagonal) {
+                    zero_below_diagonal<R>(tile, lane, row0, col0);
+                    ptx::fence_proxy_async();               // these generic writes precede the TMA refill of the slot
+                    __syncwarp();
+                }
+                sweep_block<R>(tile, v, acc, carry, bin, bout, lane);
 #pragma unroll
-                    for (int i = 0; i < R; ++i) bits_s[cb * plan.rows + row0 + i] = acc[i];
+                for (int i = 0; i < R; ++i) acc[i] = __brev(acc[i]);   // first frame came in first: bit 31 -> bit 0
+                if (on_diagonal) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        // the forced step on the diagonal (frame == token, core.pyx:34), tokens > 0 only
+                        const int d = row0 + i - col0;
+                        if (d >= 0 && d < kBlk && row0 + i > 0) acc[i] |= 1u << d;
+                    }
+                }
+                if (bits_smem) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) bits_s[cb * rows + row0 + i] = acc[i];
                 } else {
 #pragma unroll
-                    for (int i = 0; i < R; ++i) bits_g[(size_t)cb * plan.rows + row0 + i] = acc[i];
+                    for (int i = 0; i < R; ++i) bits_g[(size_t)cb * rows + row0 + i] = acc[i];
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    if (cb + S <= cbend) {
-                        ptx::mbar_arrive_expect_tx(&my_full[slot], box_bytes);
-                        ptx::tma_load_3d(my_ring + (size_t)slot * rows_per_warp * kBlk, &tmap, &my_full[slot], (cb + S) * kBlk, x0, b);
-                    }
-                    ptx::st_release_shared(&done[warp], cb + 1);
+                // lane 0, predicated (no divergent region): refill the ring slot, publish progress
+                ptx::tma_load_3d_if(lane0 && cb + S <= cbend, my_ring + (size_t)slot * rows_per_warp * kBlk, &tmap,
+                                    &my_full[slot], box_bytes, (cb + S) * kBlk, x0, b);
+                ptx::st_release_shared_if(lane0, &done[warp], cb + 1);
+                if (++slot == S) {
+                    slot = 0;
+                    parity ^= 1u;
                 }
-                if (dbg) {
-                    t_sweep += t5 - t4;
-                    t_tail += clock64() - t5;
+                if (kDbg) {
+                    t_wait_prev += t2 - t0;
+                    t_wait_tma += t3 - t2;
+                    t_sweep += clock64() - t3;
                 }
             }
             __syncwarp();
             if (lane == 0) ptx::st_release_shared(&done[warp], kDoneAll);
+            // a NaN or an infinity anywhere in this token's history is still in its score now
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                if (row0 + i < tx && !(fabsf(v[i]) <= 3.402823466e38f)) nonfinite = 1;
         }
-        if (dbg && lane == 0) {
+        if (kDbg && dbg && lane == 0) {
             dbg[1] = clock64();
             dbg[2] = t_wait_prev;
             dbg[3] = t_wait_next;
             dbg[4] = t_wait_tma;
             dbg[8] = t_sweep;
-            dbg[9] = t_tail;
             dbg[10] = cbend - cb0 + 1;
         }
     } else {
         // ---- filler warp: zero the dense output while the sweep runs ----
-        float4 *o4 = reinterpret_cast<float4 *>(p.path + (int64_t)b * T_x * T_y);
-        const int64_t n4 = ((int64_t)T_x * T_y) >> 2;            // T_y % 4 == 0 on this path
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        int64_t i = lane;
-        for (; i + 96 < n4; i += 128) {
-            ptx::st_global_cs_v4(o4 + i, z4);
-            ptx::st_global_cs_v4(o4 + i + 32, z4);
-            ptx::st_global_cs_v4(o4 + i + 64, z4);
-            ptx::st_global_cs_v4(o4 + i + 96, z4);
-        }
-        for (; i < n4; i += 32) ptx::st_global_cs_v4(o4 + i, z4);
-        if (dbg && lane == 0) dbg[1] = clock64();
-    }
-    if (!plan.bits_in_smem) __threadfence_block();
-    __syncthreads();
-
-    // ---- backtrack (core.pyx:32-35) by TOKENS, warp 0 in lockstep ----
-    // State: the path sits on token x for frames (.., y_hi]; ys <= y_hi is how far left that run has
-    // been scanned without finding the frame where the path stepped onto x.  Lane k holds the
-    // direction word of token x-k for the current 32-frame block, so a block is fetched with one
-    // load and every further token costs a shuffle + count-leading-zeros instead of a memory trip.
-    // Stepping is forced on the diagonal (frame == token, core.pyx:34 `index == y`).
-    if (dbg && tid == 0) dbg[5] = clock64();
-    if (warp == 0 && tx > 0) {
-        int x = tx - 1, y_hi = ty - 1, ys = ty - 1;
-        while (x > 0) {
-            const int cb = ys >> 5;
-            const int r = x - lane;
-            uint32_t wd = 0u;
-            if (r > 0) wd = plan.bits_in_smem ? bits_s[cb * plan.rows + r] : __ldcg(bits_g + (size_t)cb * plan.rows + r);
-#pragma unroll 4
-            for (int k = 0; k < 32; ++k) {
-                const uint32_t w = __shfl_sync(0xffffffffu, wd, k);
-                const uint32_t m = w & (0xffffffffu >> (31 - (ys & 31)));
-                int ylo = (m != 0u) ? (cb << 5) + 31 - __clz(m) : -1;
-                ylo = max(ylo, x);
-                if (ylo < (cb << 5)) {          // stepped onto x in an earlier block: same token, next block
-                    ys = (cb << 5) - 1;
-                    break;
-                }
-                if (lane == 0) run[x] = make_int2(ylo, y_hi);
-                y_hi = ys = ylo - 1;
-                --x;
-                if (x == 0 || (ys >> 5) != cb) break;
+        // One lane streams a shared zero page to global memory with bulk async copies (UBLKCP):
+        // ~50 instructions for the whole slab instead of a flood of vector stores that would
+        // compete with the sweep warps for the load/store pipe.
+        float4 *zero4 = reinterpret_cast<float4 *>(smem + plan.off_zero);
+        for (int i = lane; i < kZeroBytes / 16; i += 32) zero4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ptx::fence_proxy_async();                              // generic writes -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) {
+            char *dst = reinterpret_cast<char *>(p.path + (int64_t)b * T_x * T_y);
+            const int64_t total = (int64_t)T_x * T_y * 4;        // multiple of 16: T_y % 4 == 0 on this path
+            for (int64_t off = 0; off < total; off += kZeroBytes) {
+                const int64_t n = total - off;
+                ptx::bulk_store_s2g(dst + off, zero4, (uint32_t)(n < kZeroBytes ? n : kZeroBytes));
             }
+            ptx::bulk_commit_group();
+            ptx::bulk_wait_all();                              // the ones are written after the next barrier
         }
-        if (lane == 0) run[0] = make_int2(0, y_hi);
+        __syncwarp();
+        if (kDbg && dbg && lane == 0) dbg[1] = clock64();
     }
-    if (dbg && tid == 0) dbg[6] = clock64();
+    if (!bits_smem) __threadfence_block();
+    const int redo = __syncthreads_or(nonfinite);
+    if (redo) {
+        // non-finite scores: the sign trick is not the reference's compare there -- redo literally
+        float *col = reinterpret_cast<float *>(smem + plan.off_ring);
+        const float *val = p.value + (int64_t)b * p.value_stride_b;
+        if (bits_smem)
+            exact_sweep_cta<true>(val, p.value_stride_x, col, bits_s, rows, tx, ty, p.max_neg_val);
+        else
+            exact_sweep_cta<false>(val, p.value_stride_x, col, bits_g, rows, tx, ty, p.max_neg_val);
+        if (!bits_smem) __threadfence_block();
+        __syncthreads();
+    }
+
+    // ---- backtrack (core.pyx:32-35) by TOKENS ----
+    if (kDbg && dbg && tid == 0) dbg[5] = clock64();
+    if (tid == 0 && tx > 0) {
+        if (bits_smem)
+            backtrack_tokens<true>(bits_s, rows, tx, ty, run);
+        else
+            backtrack_tokens<false>(bits_g, rows, tx, ty, run);
+    }
+    if (kDbg && dbg && tid == 0) dbg[6] = clock64();
     __syncthreads();
 
     // ---- dense path: ones, durations, frame -> token ----
@@ -370,7 +494,7 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
     }
     if (p.frame_token)
         for (int y = ty + tid; y < T_y; y += blockDim.x) p.frame_token[(int64_t)b * T_y + y] = -1;
-    if (dbg && lane == 0) dbg[7] = clock64();
+    if (kDbg && dbg && lane == 0) dbg[7] = clock64();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -390,6 +514,10 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
+// Tokens per lane (R) and sweep warps (W).  A lone warp issues about one instruction every two
+// cycles, so the per-frame cost is ~2 x (4R + 5) cycles, and never below the shuffle round trip
+// amortised over R frames (~(29 + 10R)/R): R = 2..4 with at most one sweep warp per scheduler is the
+// sweet spot; longer texts take more tokens per lane first, more warps second.
 static bool choose_shape(int T_x, int &R, int &W) {
     const int groups = ceil_div(T_x, kBlk);            // 32-token groups
     if (groups <= 1) {
@@ -397,23 +525,42 @@ static bool choose_shape(int T_x, int &R, int &W) {
         W = 1;
         return true;
     }
-    for (int r : {3, 5}) {
-        const int w = ceil_div(groups, r);
-        if (w <= kMaxDpWarps) {
-            R = r;
-            W = w;
-            return true;
+    for (int max_w : {4, 8, kMaxDpWarps})
+        for (int r : {2, 3, 4, 5, 6, 8}) {
+            const int w = ceil_div(groups, r);
+            if (w <= max_w) {
+                R = r;
+                W = w;
+                return true;
+            }
         }
-    }
     return false;
+}
+
+template <int R, int kThreads>
+static int launch_rt(const CUtensorMap &tmap, const PathParams &p, const Plan &plan, cudaStream_t stream) {
+    static int configured_smem[64] = {0};             // opt-in attribute is sticky per device: raise it only when needed
+    int dev = 0;
+    MAS_CUDA_TRY(cudaGetDevice(&dev));
+    if (p.dbg_cycles != nullptr) {                    // profiling build of the same kernel (clock64 stamps)
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_path_systolic_kernel<R, kThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.total));
+        mas_path_systolic_kernel<R, kThreads, true><<<p.B, (plan.W + 1) * 32, plan.total, stream>>>(tmap, p, plan);
+        MAS_CUDA_TRY(cudaGetLastError());
+        return MAS_OK;
+    }
+    if (plan.total > configured_smem[dev & 63]) {
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_path_systolic_kernel<R, kThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.total));
+        configured_smem[dev & 63] = plan.total;
+    }
+    mas_path_systolic_kernel<R, kThreads, false><<<p.B, (plan.W + 1) * 32, plan.total, stream>>>(tmap, p, plan);
+    MAS_CUDA_TRY(cudaGetLastError());
+    return MAS_OK;
 }
 
 template <int R>
 static int launch_r(const CUtensorMap &tmap, const PathParams &p, const Plan &plan, cudaStream_t stream) {
-    MAS_CUDA_TRY(cudaFuncSetAttribute(mas_path_systolic_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.total));
-    mas_path_systolic_kernel<R><<<p.B, (plan.W + 1) * 32, plan.total, stream>>>(tmap, p, plan);
-    MAS_CUDA_TRY(cudaGetLastError());
-    return MAS_OK;
+    if (plan.W <= 4) return launch_rt<R, 160>(tmap, p, plan, stream);
+    return launch_rt<R, (kMaxDpWarps + 1) * 32>(tmap, p, plan, stream);
 }
 
 }  // namespace systolic
@@ -438,17 +585,20 @@ int launch_path_systolic(PathParams p, void *workspace, size_t workspace_bytes, 
     PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode_fn();
     if (encode == nullptr) return MAS_ERR_UNSUPPORTED_SHAPE;
 
-    int dev = 0, max_smem = 0;
+    static int max_smem_cached[64] = {0};
+    int dev = 0;
     MAS_CUDA_TRY(cudaGetDevice(&dev));
-    MAS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    max_smem -= 2048;   // static shared + alignment slack
+    if (dev < 0 || dev >= 64) return MAS_ERR_INVALID_ARGUMENT;
+    if (max_smem_cached[dev] == 0)
+        MAS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem_cached[dev], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int max_smem = max_smem_cached[dev] - 2048;   // static shared + alignment slack
     // deepest ring that fits, bits in shared memory if possible
     Plan plan{};
     bool ok = false;
     for (int bits_smem = 1; bits_smem >= 0 && !ok; --bits_smem)
         for (int S = 4; S >= 2; --S) {
             plan = make_plan(R, W, S, p.T_y, bits_smem != 0);
-            if (plan.total <= max_smem && (bits_smem || S >= 3 || true)) {
+            if (plan.total <= max_smem) {
                 ok = true;
                 break;
             }
@@ -472,8 +622,12 @@ int launch_path_systolic(PathParams p, void *workspace, size_t workspace_bytes, 
 
     switch (R) {
         case 1: return launch_r<1>(tmap, p, plan, stream);
+        case 2: return launch_r<2>(tmap, p, plan, stream);
         case 3: return launch_r<3>(tmap, p, plan, stream);
+        case 4: return launch_r<4>(tmap, p, plan, stream);
         case 5: return launch_r<5>(tmap, p, plan, stream);
+        case 6: return launch_r<6>(tmap, p, plan, stream);
+        case 8: return launch_r<8>(tmap, p, plan, stream);
         default: return MAS_ERR_UNSUPPORTED_SHAPE;
     }
 }

@@ -53,9 +53,44 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Predicated "arm the barrier, then issue the box load": no branch, so a warp that runs alone on its
+// scheduler does not pay a divergent region just for lane 0 to talk to the TMA unit.
+__device__ __forceinline__ void tma_load_3d_if(bool pred, void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                               uint32_t bytes, int c0, int c1, int c2) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %0, 0;\n"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %4;\n"
+        "@p cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%1], [%2, {%5, %6, %7}], [%3];\n"
+        "}\n"
+        ::"r"((uint32_t)pred), "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+          "r"(bytes), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void st_release_shared_if(bool pred, int *p, int v) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %0, 0;\n"
+        "@p st.release.cta.shared.s32 [%1], %2;\n"
+        "}\n"
+        ::"r"((uint32_t)pred), "r"(smem_u32(p)), "r"(v)
+        : "memory");
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+
+// ---- bulk (non-tensor) async copy shared -> global, bulk-group completion ----------------------
+__device__ __forceinline__ void bulk_store_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// waits until every committed bulk group has completed (its global writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- acquire / release flags in shared memory -------------------------------------------------
 __device__ __forceinline__ int ld_acquire_shared(const int *p) {
