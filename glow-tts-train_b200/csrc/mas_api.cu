@@ -59,6 +59,8 @@ int mas_b200_last_cuda_error(void) { return g_last_cuda_error; }
 
 void mas_b200_debug_set_cycle_buffer(void *device_buffer) { g_dbg_cycles = static_cast<long long *>(device_buffer); }
 
+void mas_b200_debug_force_cluster(int ctas_per_utterance) { path_systolic_force_cluster(ctas_per_utterance); }
+
 int mas_b200_device_ok(void) {
     int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return MAS_ERR_NO_DEVICE;

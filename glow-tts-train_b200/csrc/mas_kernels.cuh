@@ -35,6 +35,7 @@ int launch_path_simple(PathParams p, void *workspace, size_t workspace_bytes, cu
 size_t path_systolic_workspace_bytes(int B, int T_x, int T_y);
 // MAS_ERR_UNSUPPORTED_SHAPE = "not for the TMA path": the caller falls back to launch_path_simple.
 int launch_path_systolic(PathParams p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+void path_systolic_force_cluster(int k);   // testing hook: CTAs per utterance (0 = heuristic)
 
 // developer profiling hook: when non-null, kernels stamp clock64() phase times into it
 extern long long *g_dbg_cycles;

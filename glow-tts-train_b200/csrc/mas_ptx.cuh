@@ -102,6 +102,70 @@ __device__ __forceinline__ void st_release_shared(int *p, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
+// ---- thread-block clusters: rank, barrier, distributed shared memory ---------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// every thread of every CTA of the cluster; release/acquire at cluster scope
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same variable in CTA `rank`
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4_if(bool pred, uint32_t addr, float4 v) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %0, 0;\n"
+        "@p st.shared::cluster.v4.f32 [%1], {%2, %3, %4, %5};\n"
+        "}\n"
+        ::"r"((uint32_t)pred), "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+        : "memory");
+}
+__device__ __forceinline__ void st_shared_v4_if(bool pred, uint32_t addr, float4 v) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %0, 0;\n"
+        "@p st.shared.v4.f32 [%1], {%2, %3, %4, %5};\n"
+        "}\n"
+        ::"r"((uint32_t)pred), "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+        : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cluster_if(bool pred, uint32_t addr, int v) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %0, 0;\n"
+        "@p st.release.cluster.shared::cluster.s32 [%1], %2;\n"
+        "}\n"
+        ::"r"((uint32_t)pred), "r"(addr), "r"(v)
+        : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cluster_shared(const int *p) {
+    int v;
+    asm volatile("ld.acquire.cluster.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
 // ---- streaming (evict-first) 16-byte global store ---------------------------------------------
 __device__ __forceinline__ void st_global_cs_v4(float4 *p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

@@ -57,6 +57,9 @@ int mas_b200_last_cuda_error(void);
 /* Developer profiling hook: when `device_buffer` (int64 [B][16][16], device memory) is non-NULL the
  * kernels stamp clock64() phase boundaries per warp into it; NULL (the default) switches it off. */
 void mas_b200_debug_set_cycle_buffer(void *device_buffer);
+/* Testing hook: force the number of CTAs (thread-block cluster size: 1, 2, 4, 8) that share one
+ * utterance in kernel (1); 0 restores the heuristic. */
+void mas_b200_debug_force_cluster(int ctas_per_utterance);
 /* MAS_OK iff the current CUDA device can run the kernels (compute capability 10.x). */
 int mas_b200_device_ok(void);
 

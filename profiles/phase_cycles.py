@@ -25,7 +25,9 @@ ty = torch.full((B,), T_y, dtype=torch.int32, device=dev)
 for v in vals:
     pkg.maximum_path_from_lengths(v, tx, ty)
 torch.cuda.synchronize()
-buf = torch.zeros(B, 16, 16, dtype=torch.int64, device=dev)
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 0          # CTAs per utterance (0 = heuristic)
+lib.mas_b200_debug_force_cluster(K)
+buf = torch.zeros(B * 8, 16, 16, dtype=torch.int64, device=dev)
 lib.mas_b200_debug_set_cycle_buffer(buf.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
@@ -34,6 +36,7 @@ e1.record()
 torch.cuda.synchronize()
 lib.mas_b200_debug_set_cycle_buffer(None)
 d = buf.cpu().numpy()
+d = d[d[:, :, 0].any(axis=1)]                                # CTAs that ran
 print(f"shape B={B} T_x={T_x} T_y={T_y}; event time {e0.elapsed_time(e1) * 1e3:.1f} us")
 t0 = d[:, :, 0].copy()
 t0[t0 == 0] = np.iinfo(np.int64).max
@@ -45,5 +48,6 @@ for w in range(16):
     print(f"warp {w:2d}: start +{np.median(d[:, w, 0] - start):8.0f}  sweep/fill {sweep:9.0f} cyc   "
           f"wait prev {np.median(d[:, w, 2]):8.0f}  next {np.median(d[:, w, 3]):8.0f}  tma {np.median(d[:, w, 4]):8.0f}"
           f"  | blocks {np.median(d[:, w, 10]):4.0f} compute {np.median(d[:, w, 8]):8.0f} tail {np.median(d[:, w, 9]):7.0f}")
+print(f"{len(d)} CTAs ({len(d) // B} per utterance)")
 print(f"CTA: barrier1 at +{np.median(d[:, 0, 5] - start):.0f}, backtrack {np.median(d[:, 0, 6] - d[:, 0, 5]):.0f} cyc, "
       f"end at +{np.median(d[:, 0, 7] - start):.0f} cyc")

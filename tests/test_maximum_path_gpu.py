@@ -202,3 +202,33 @@ def test_full_size_parity_and_properties(pkg, oracle, shape):
         assert p[b, t_x[b]:].sum() == 0 and p[b, :, t_y[b]:].sum() == 0
     want = oracle.maximum_path(value, t_x, t_y, threads=oracle.host_threads())
     assert np.array_equal(p, want)
+
+
+@pytest.mark.parametrize("K", [1, 2, 4, 8])
+@pytest.mark.parametrize("shape", [(3, 64, 256), (4, 200, 1000), (2, 257, 640), (2, 512, 1024), (1, 1024, 2048)])
+def test_cluster_sharded_tokens(pkg, oracle, shape, K):
+    """Kernel (1) with the utterance's tokens sharded over a thread-block cluster of K CTAs (forced
+    through the testing hook): boundary scores, progress and the backtrack hand-over travel over
+    distributed shared memory.  Same bits as one CTA, same bits as the oracle."""
+    lib = pkg._lib.load()
+    B, T_x, T_y = shape
+    if T_x // K < 32:
+        pytest.skip("fewer than 32 tokens per CTA")
+    rng = np.random.default_rng(zlib.crc32(repr((shape, K)).encode()))
+    value = (10 * rng.standard_normal(shape) - 100).astype(np.float32)
+    t_x, t_y = ragged_lengths(rng, B, T_x, T_y)
+    if B > 1:
+        t_x[-1], t_y[-1] = max(1, T_x // 8), max(T_x // 8, T_y // 5) // 4 * 4    # leaves upper CTAs without tokens
+        value[-1, 3, 17] = np.nan                                                 # and takes the exact-redo path
+    want = oracle.maximum_path(value, t_x, t_y)
+    lib.mas_b200_debug_force_cluster(K)
+    try:
+        path, dur, tok = run_gpu(pkg, value, t_x, t_y, via_mask=False, want_durations=True, want_frame_token=True)
+        torch.cuda.synchronize()
+    finally:
+        lib.mas_b200_debug_force_cluster(0)
+    assert np.array_equal(as_i32(path), want)
+    assert np.array_equal(dur.cpu().numpy(), want.sum(-1))
+    tok = tok.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(tok[b, :t_y[b]], want[b, :, :t_y[b]].argmax(0))
