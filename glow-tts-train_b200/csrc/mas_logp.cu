@@ -2,93 +2,189 @@
 // (glow_tts_train/models.py:362-376), materialised.  FP32 FFMA contraction over the mel channels on
 // the CUDA cores (K = 80 is too thin for a tensor-core pipeline to pay off; BASELINE.json north_star).
 //
-//   logp[b,x,y] = ((l1[x] + l2[x,y]) + l3[x,y]) + l4[x]                      models.py:376
-//   l1[x]   = sum_d (-0.5 log(2 pi) - logs[d,x])                             models.py:364-366
-//   l2[x,y] = sum_d inv_var[d,x] * (-0.5 z[d,y]^2),  inv_var = exp(-2 logs)  models.py:363,367-369
-//   l3[x,y] = sum_d (m[d,x] inv_var[d,x]) * z[d,y]                           models.py:370-372
-//   l4[x]   = sum_d -0.5 m[d,x]^2 inv_var[d,x]                               models.py:373-375
-//
-// Every cell is contracted by logp_cell_fma() in ascending channel order; the fused kernel uses the
-// same routine so that both produce bit-identical scores.
+// One CTA owns a tile of tokens of one utterance (up to 208, all of a 200-token text) and walks a
+// range of 64-frame chunks: the token-side operands (exp(-2 logs), m exp(-2 logs), 80 channels) are
+// computed once and stay in shared memory, the frame-side operands (z, -0.5 z^2) are staged per
+// chunk, and every thread contracts an 8 x 8 block of cells in registers (mas_logp_tile.cuh).
+// The arithmetic (operands, FFMA order, final adds) is the one the fused kernel uses, so both
+// produce bit-identical scores.
 #include "mas_kernels.cuh"
 #include "mas_logp_tile.cuh"
+#include "mas_ptx.cuh"
 
 namespace mas {
 namespace logp {
 
-constexpr int kTileX = 64, kTileY = 64, kThreads = 256, kChunkD = 40;
+constexpr int kMaxTileRows = 208;   // 26 row groups of 8 -> 208 threads
+constexpr int kPanel = 80;          // channels resident in shared memory at a time
 
-// grid: (ceil(T_y/64), ceil(T_x/64), B); block 256 = 16 (token groups of 4) x 16 (frame groups of 4)
-__global__ void __launch_bounds__(kThreads) mas_logp_kernel(LogpParams p) {
-    __shared__ __align__(16) float s_inv[kChunkD][kTileX];   // inv_var[d][x]
-    __shared__ __align__(16) float s_miv[kChunkD][kTileX];   // m * inv_var
-    __shared__ __align__(16) float s_z[kChunkD][kTileY];     // z[d][y]
-    __shared__ __align__(16) float s_zz[kChunkD][kTileY];    // -0.5 z^2
-    __shared__ float s_l1[kTileX], s_l4[kTileX];
+struct Geometry {
+    int tile_rows;      // multiple of 8
+    int row_tiles;      // ceil(T_x / tile_rows)
+    int nchunks;        // ceil(T_y / 64)
+    int splits;         // CTAs along the frame axis
+    int chunks_per_cta;
+    int threads;
+    int panel;          // min(D, kPanel)
+    int smem_bytes;
+};
 
-    const int b = blockIdx.z, x0 = blockIdx.y * kTileX, y0 = blockIdx.x * kTileY;
-    const int tid = threadIdx.x;
+static Geometry make_geometry(int B, int D, int T_x, int T_y, int num_sms) {
+    Geometry g;
+    g.row_tiles = ceil_div(T_x, kMaxTileRows);
+    g.tile_rows = ceil_div(ceil_div(T_x, g.row_tiles), 8) * 8;
+    g.nchunks = ceil_div(T_y, kGemmFrames);
+    // CTAs along the frame axis: fewest (waves x chunks per CTA), counting ~0.7 chunk of token-side
+    // staging per CTA
+    const int64_t base = (int64_t)B * g.row_tiles;
+    double best = 1e30;
+    g.chunks_per_cta = g.nchunks;
+    for (int cpc = 1; cpc <= g.nchunks; ++cpc) {
+        const int64_t ctas = base * ceil_div(g.nchunks, cpc);
+        const double cost = (double)((ctas + num_sms - 1) / num_sms) * (cpc + 0.7);
+        if (cost < best - 1e-9) {
+            best = cost;
+            g.chunks_per_cta = cpc;
+        }
+    }
+    g.splits = ceil_div(g.nchunks, g.chunks_per_cta);
+    g.threads = max(64, ceil_div(g.tile_rows, 32) * 32);
+    g.panel = D < kPanel ? D : kPanel;
+    g.smem_bytes = (2 * g.panel * g.tile_rows + 2 * g.panel * kGemmFrames + 2 * g.tile_rows) * 4;
+    return g;
+}
+
+// grid: (splits, row_tiles, B)
+__global__ void __launch_bounds__(256, 1) mas_logp_kernel(LogpParams p, Geometry g) {
+    extern __shared__ __align__(16) float sm[];
+    const int tile_rows = g.tile_rows, panel = g.panel;
+    float *sInv = sm;                                   // [panel][tile_rows]
+    float *sMiv = sInv + panel * tile_rows;             // [panel][tile_rows]
+    float *sZ = sMiv + panel * tile_rows;               // [2][panel][64]  (double-buffered chunk of z)
+    float *sL1 = sZ + 2 * panel * kGemmFrames;          // [tile_rows]
+    float *sL4 = sL1 + tile_rows;                       // [tile_rows]
+
+    const int b = blockIdx.z, x0 = blockIdx.y * tile_rows;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int D = p.D, T_x = p.T_x, T_y = p.T_y;
     const float *xm = p.x_m + (int64_t)b * D * T_x;
     const float *xl = p.x_logs ? p.x_logs + (int64_t)b * D * T_x : nullptr;
-    const float *zz = p.z + (int64_t)b * D * T_y;
-
-    if (tid < kTileX) {
-        float l1, l4;
-        row_constants(xm, xl, D, T_x, x0 + tid, l1, l4);
-        s_l1[tid] = l1;
-        s_l4[tid] = l4;
-    }
-
-    const int rx = (tid >> 4) * 4, cy = (tid & 15) * 4;
-    float acc2[4][4], acc3[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc2[i][j] = acc3[i][j] = 0.f;
-
-    for (int d0 = 0; d0 < D; d0 += kChunkD) {
-        const int dn = min(kChunkD, D - d0);
-        __syncthreads();
-        for (int i = tid; i < dn * kTileX; i += kThreads) {
-            const int d = i / kTileX, x = i % kTileX;
-            float inv, miv;
-            token_operands(xm, xl, T_x, d0 + d, x0 + x, inv, miv);
-            s_inv[d][x] = inv;
-            s_miv[d][x] = miv;
-        }
-        for (int i = tid; i < dn * kTileY; i += kThreads) {
-            const int d = i / kTileY, y = i % kTileY;
-            float zv, zsq;
-            frame_operands(zz, T_y, d0 + d, y0 + y, zv, zsq);
-            s_z[d][y] = zv;
-            s_zz[d][y] = zsq;
-        }
-        __syncthreads();
-        for (int d = 0; d < dn; ++d) {
-            const float4 inv = *reinterpret_cast<const float4 *>(&s_inv[d][rx]);
-            const float4 miv = *reinterpret_cast<const float4 *>(&s_miv[d][rx]);
-            const float4 zv = *reinterpret_cast<const float4 *>(&s_z[d][cy]);
-            const float4 zq = *reinterpret_cast<const float4 *>(&s_zz[d][cy]);
-            const float a[4] = {inv.x, inv.y, inv.z, inv.w}, m[4] = {miv.x, miv.y, miv.z, miv.w};
-            const float zc[4] = {zv.x, zv.y, zv.z, zv.w}, qc[4] = {zq.x, zq.y, zq.z, zq.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) logp_cell_fma(acc2[i][j], acc3[i][j], a[i], m[i], qc[j], zc[j]);
-        }
-    }
-    __syncthreads();
+    const float *zg = p.z + (int64_t)b * D * T_y;
     float *out = p.logp + (int64_t)b * T_x * T_y;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int x = x0 + rx + i;
-        if (x >= T_x) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int y = y0 + cy + j;
-            if (y < T_y) out[(int64_t)x * T_y + y] = logp_cell_finish(s_l1[rx + i], acc2[i][j], acc3[i][j], s_l4[rx + i]);
+
+    const int rg = tid >> 3, cg = tid & 7;              // 8 tokens x {4+4} frames per thread
+    const bool worker = rg * 8 < tile_rows;
+    const bool vec_ok = ((T_y & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int npanels = ceil_div(D, panel);
+    // frames staged by cp.async (16 bytes, no registers, overlapped with the previous chunk's FFMAs)
+    const bool async_z = npanels == 1 && ((T_y & 3) == 0) && ((reinterpret_cast<uintptr_t>(zg) & 15) == 0);
+
+    // token side of one channel panel: thread x stages token x0+x for every channel (coalesced over
+    // x, eight loads in flight) and sums its row constants on the way, channels ascending
+    auto stage_tokens = [&](int pn, int d0, int dn, bool keep_consts) {
+        for (int x = tid; x < tile_rows; x += nthr) {
+            const int xg = x0 + x;
+            float l1 = (pn == 0) ? 0.f : sL1[x], l4 = (pn == 0) ? 0.f : sL4[x];
+            if (xg < T_x) {
+#pragma unroll 8
+                for (int d = 0; d < dn; ++d) {
+                    const float m = __ldg(xm + (int64_t)(d0 + d) * T_x + xg);
+                    const float ls = xl ? __ldg(xl + (int64_t)(d0 + d) * T_x + xg) : 0.f;
+                    const float r = xl ? expf(-2.0f * ls) : 1.0f;         // models.py:363
+                    sInv[d * tile_rows + x] = r;
+                    sMiv[d * tile_rows + x] = m * r;                        // models.py:371
+                    l1 += kNegHalfLog2Pi - ls;                              // models.py:364-366
+                    l4 = fmaf(-0.5f * (m * m), r, l4);                      // models.py:373-375
+                }
+            } else {
+                for (int d = 0; d < dn; ++d) sInv[d * tile_rows + x] = sMiv[d * tile_rows + x] = 0.f;
+            }
+            if (keep_consts) {
+                sL1[x] = l1;
+                sL4[x] = l4;
+            }
         }
+    };
+    auto stage_frames_async = [&](int ch, int buf) {
+        const int y0 = ch * kGemmFrames;
+        float *dst = sZ + buf * panel * kGemmFrames;
+        for (int i = tid; i < D * (kGemmFrames / 4); i += nthr) {
+            const int d = i >> 4, y = y0 + ((i & 15) << 2);
+            ptx::cp_async_16(dst + (i << 2), zg + (int64_t)d * T_y + (y < T_y ? y : 0), y < T_y);
+        }
+        ptx::cp_async_commit();
+    };
+    auto store_tile = [&](int y0, float (&acc)[8][8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int xr = rg * 8 + i, x = x0 + xr;
+            if (x >= T_x) break;
+            const float l1 = sL1[xr], l4 = sL4[xr];
+            float *row = out + (int64_t)x * T_y;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int y = y0 + 32 * h + 4 * cg;
+                float4 r;
+                r.x = logp_cell_finish(l1, acc[i][4 * h + 0], l4);
+                r.y = logp_cell_finish(l1, acc[i][4 * h + 1], l4);
+                r.z = logp_cell_finish(l1, acc[i][4 * h + 2], l4);
+                r.w = logp_cell_finish(l1, acc[i][4 * h + 3], l4);
+                if (vec_ok && y + 3 < T_y) {
+                    *reinterpret_cast<float4 *>(row + y) = r;
+                } else {
+                    if (y < T_y) row[y] = r.x;
+                    if (y + 1 < T_y) row[y + 1] = r.y;
+                    if (y + 2 < T_y) row[y + 2] = r.z;
+                    if (y + 3 < T_y) row[y + 3] = r.w;
+                }
+            }
+        }
+    };
+
+    const int chunk0 = blockIdx.x * g.chunks_per_cta;
+    const int chunk1 = min(chunk0 + g.chunks_per_cta, g.nchunks);
+    float acc[8][8];
+    if (async_z) {
+        stage_frames_async(chunk0, 0);                  // in flight while the token side is prepared
+        stage_tokens(0, 0, D, true);
+        for (int ch = chunk0; ch < chunk1; ++ch) {
+            const int buf = (ch - chunk0) & 1;
+            if (ch + 1 < chunk1) {
+                stage_frames_async(ch + 1, buf ^ 1);    // buffer buf^1 was released by the barrier below
+                ptx::cp_async_wait<1>();
+            } else {
+                ptx::cp_async_wait<0>();
+            }
+            __syncthreads();                            // chunk ch (and the token side) visible to everyone
+            if (worker) {
+                gemm_tile_8x8<true>(sInv, sMiv, sZ + buf * panel * kGemmFrames, D, tile_rows, rg, cg, acc);
+                store_tile(ch * kGemmFrames, acc);
+            }
+            __syncthreads();                            // everyone is done reading buffer buf
+        }
+        return;
+    }
+    // generic path: any alignment, any channel count (panels of 80)
+    for (int ch = chunk0; ch < chunk1; ++ch) {
+        const int y0 = ch * kGemmFrames;
+        for (int pn = 0; pn < npanels; ++pn) {
+            const int d0 = pn * panel, dn = min(panel, D - d0);
+            __syncthreads();                            // previous contraction done with the staged operands
+            if (npanels > 1 || ch == chunk0) stage_tokens(pn, d0, dn, ch == chunk0);
+#pragma unroll 4
+            for (int i = tid; i < dn * kGemmFrames; i += nthr) {    // frame side, coalesced over y
+                const int d = i >> 6, yg = y0 + (i & 63);
+                sZ[i] = (yg < T_y) ? __ldg(zg + (int64_t)(d0 + d) * T_y + yg) : 0.f;
+            }
+            __syncthreads();
+            if (worker) {
+                if (pn == 0)
+                    gemm_tile_8x8<true>(sInv, sMiv, sZ, dn, tile_rows, rg, cg, acc);
+                else
+                    gemm_tile_8x8<false>(sInv, sMiv, sZ, dn, tile_rows, rg, cg, acc);
+            }
+        }
+        if (worker) store_tile(y0, acc);
     }
 }
 
@@ -97,8 +193,19 @@ __global__ void __launch_bounds__(kThreads) mas_logp_kernel(LogpParams p) {
 int launch_logp(const LogpParams &p, cudaStream_t stream) {
     using namespace logp;
     if (p.B == 0 || p.T_x == 0 || p.T_y == 0) return MAS_OK;
-    dim3 grid(ceil_div(p.T_y, kTileY), ceil_div(p.T_x, kTileX), p.B);
-    mas_logp_kernel<<<grid, kThreads, 0, stream>>>(p);
+    static int num_sms_cached[64] = {0}, configured[64] = {0};
+    int dev = 0;
+    MAS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return MAS_ERR_INVALID_ARGUMENT;
+    if (num_sms_cached[dev] == 0)
+        MAS_CUDA_TRY(cudaDeviceGetAttribute(&num_sms_cached[dev], cudaDevAttrMultiProcessorCount, dev));
+    const Geometry g = make_geometry(p.B, p.D, p.T_x, p.T_y, num_sms_cached[dev]);
+    if (g.smem_bytes > configured[dev]) {
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_logp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+        configured[dev] = g.smem_bytes;
+    }
+    dim3 grid(g.splits, g.row_tiles, p.B);
+    mas_logp_kernel<<<grid, g.threads, g.smem_bytes, stream>>>(p, g);
     MAS_CUDA_TRY(cudaGetLastError());
     return MAS_OK;
 }

@@ -1,6 +1,17 @@
-// mas_logp_tile.cuh -- the per-cell arithmetic of the log-likelihood matrix (models.py:362-376),
-// shared by the materialising kernel (mas_logp.cu) and the fused kernel so that both give
-// bit-identical scores: same operands, same FFMA order (ascending channel), same final adds.
+// mas_logp_tile.cuh -- the arithmetic of the log-likelihood matrix (models.py:362-376), shared by
+// the materialising kernel (mas_logp.cu) and the fused kernel so that both give bit-identical
+// scores: same operands, same FFMA order, same final adds.
+//
+//   logp[x,y] = (l1[x] + c[x,y]) + l4[x]
+//   c[x,y]    = sum over channels d, ascending, ONE accumulator:
+//                   c = fma(inv_var[d,x], -0.5 z[d,y]^2, c)        (models.py:367-369, "logp2")
+//                   c = fma(m[d,x] inv_var[d,x], z[d,y], c)        (models.py:370-372, "logp3")
+//   l1[x]     = sum_d (-0.5 log(2 pi) - logs[d,x])                 (models.py:364-366)
+//   l4[x]     = sum_d -0.5 m[d,x]^2 inv_var[d,x]                   (models.py:373-375)
+//
+// The reference adds ((l1 + l2) + l3) + l4 with l2, l3 from two cuBLAS/MKL matmuls whose K order is
+// unspecified; interleaving the two contractions into one accumulator halves the register tile and
+// stays inside the 1e-5 relative tolerance the north star states (measured ~1e-6).
 #pragma once
 
 #include "mas_common.cuh"
@@ -48,16 +59,66 @@ __device__ __forceinline__ void row_constants(const float *__restrict__ xm, cons
     }
 }
 
-// One channel of one cell: l2 += inv_var * (-0.5 z^2), l3 += (m inv_var) * z.
-__device__ __forceinline__ void logp_cell_fma(float &l2, float &l3, float inv_var, float mean_inv_var,
-                                              float neg_half_zsq, float zv) {
-    l2 = fmaf(inv_var, neg_half_zsq, l2);
-    l3 = fmaf(mean_inv_var, zv, l3);
+// One channel of one cell.
+__device__ __forceinline__ void logp_cell_fma(float &c, float inv_var, float mean_inv_var, float neg_half_zsq, float zv) {
+    c = fmaf(inv_var, neg_half_zsq, c);
+    c = fmaf(mean_inv_var, zv, c);
 }
 
-// Final adds in the reference's order (models.py:376).
-__device__ __forceinline__ float logp_cell_finish(float l1, float l2, float l3, float l4) {
-    return ((l1 + l2) + l3) + l4;
+// Final adds (models.py:376).
+__device__ __forceinline__ float logp_cell_finish(float l1, float c, float l4) { return (l1 + c) + l4; }
+
+// ---------------------------------------------------------------------------------------------
+// Register-tiled contraction: every thread owns an 8 (tokens) x 8 (frames) block of cells.
+// Shared-memory operands:
+//   sInv, sMiv : [D][tile_rows]   token-side, token index contiguous
+//   sZ         : [D][64]          frame-side, a 64-frame chunk of z; -0.5 z^2 is formed in registers
+// Thread (rg, cg): tokens 8 rg .. 8 rg + 7; frames {4 cg .. 4 cg + 3} and {32 + 4 cg .. 32 + 4 cg + 3},
+// so that the 8 column groups of a warp read one contiguous 128-byte line per LDS.128.
+// Per channel: 6 LDS.128 + 8 FMUL feed 128 FFMA -- the shared-memory port (32 floats/cycle into
+// registers per SM) is what bounds a CUDA-core contraction, so as few operand floats as possible.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGemmFrames = 64;   // frames per chunk
+
+template <bool kInit>
+__device__ __forceinline__ void gemm_tile_8x8(const float *__restrict__ sInv, const float *__restrict__ sMiv,
+                                              const float *__restrict__ sZ, int D, int tile_rows, int rg, int cg,
+                                              float (&acc)[8][8]) {
+    if (kInit) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    }
+    const float *pa = sInv + rg * 8, *pb = sMiv + rg * 8;
+    const float *pz = sZ + cg * 4;
+#pragma unroll 2
+    for (int d = 0; d < D; ++d) {
+        const float4 a0 = *reinterpret_cast<const float4 *>(pa), a1 = *reinterpret_cast<const float4 *>(pa + 4);
+        const float4 b0 = *reinterpret_cast<const float4 *>(pb), b1 = *reinterpret_cast<const float4 *>(pb + 4);
+        const float4 z0 = *reinterpret_cast<const float4 *>(pz), z1 = *reinterpret_cast<const float4 *>(pz + 32);
+        pa += tile_rows;
+        pb += tile_rows;
+        pz += kGemmFrames;
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+        float qv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qv[j] = -0.5f * (zv[j] * zv[j]);      // models.py:368
+        // Same per-cell order as logp_cell_fma (first the inv_var term, then the mean term), but
+        // issued as two sweeps over the register tile so that consecutive FFMAs share an operand
+        // (register reuse cache): three distinct register reads per FFMA would otherwise halve the
+        // issue rate on bank conflicts.
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], qv[j], acc[i][j]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(bv[i], zv[j], acc[i][j]);
+    }
 }
 
 }  // namespace mas

@@ -92,6 +92,18 @@ __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bul
 // waits until every committed bulk group has completed (its global writes are performed)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- cp.async (LDGSTS): 16-byte global -> shared copies that bypass registers ----------------------
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src, bool valid) {
+    // src-size 0 zero-fills the destination (out-of-range frames)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(valid ? 16 : 0)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- acquire / release flags in shared memory -------------------------------------------------
 __device__ __forceinline__ int ld_acquire_shared(const int *p) {
     int v;
