@@ -233,7 +233,7 @@ def run_ours(args):
             return pkg.maximum_path_from_lengths(lp, tx, ty, want_durations=True)
         return pkg.fused_maximum_path(s[0], s[1], s[2], s[3], s[4])
 
-    launches_per_step = 1 if standalone else 2   # round-1: logp kernel + path kernel
+    launches_per_step = 1                        # kernel (1) alone | the single fused launch (plus a 4 KB flag memset)
 
     def barrier():
         if dist is not None:

@@ -11,6 +11,7 @@ namespace mas {
 thread_local int g_last_cuda_error = 0;
 long long *g_dbg_cycles = nullptr;
 }
+static int g_force_unfused = 0;   // testing hook: run the two kernels back to back
 
 using namespace mas;
 
@@ -61,6 +62,8 @@ void mas_b200_debug_set_cycle_buffer(void *device_buffer) { g_dbg_cycles = stati
 
 void mas_b200_debug_force_cluster(int ctas_per_utterance) { path_systolic_force_cluster(ctas_per_utterance); }
 
+void mas_b200_debug_force_unfused(int on) { g_force_unfused = on; }
+
 int mas_b200_device_ok(void) {
     int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return MAS_ERR_NO_DEVICE;
@@ -78,7 +81,8 @@ size_t mas_b200_fused_workspace_bytes(int B, int D, int T_x, int T_y) {
     (void)D;
     if (!shape_ok(B, T_x, T_y)) return 0;
     FusedWorkspace w = fused_ws(B, T_x, T_y);
-    return w.logp_bytes + w.path_ws_bytes;
+    const size_t two_kernels = w.logp_bytes + w.path_ws_bytes, one_launch = fused_workspace_bytes(B, D, T_x, T_y);
+    return two_kernels > one_launch ? two_kernels : one_launch;
 }
 
 int mas_b200_maximum_path_f32(const float *value, int64_t value_stride_b, int64_t value_stride_x,
@@ -140,9 +144,16 @@ int mas_b200_fused_maximum_path_f32(const float *x_m, const float *x_logs, const
     if (x_m == nullptr || z == nullptr || path == nullptr || x_len == nullptr || y_len == nullptr)
         return MAS_ERR_INVALID_ARGUMENT;
     FusedWorkspace w = fused_ws(B, T_x, T_y);
-    if (workspace == nullptr || workspace_bytes < w.logp_bytes + w.path_ws_bytes) return MAS_ERR_WORKSPACE_TOO_SMALL;
-    // ROUND-1 STATE: two launches (score matrix staged in the workspace, L2-resident for the
-    // training shapes).  The single-kernel variant replaces this body; the ABI does not change.
+    if (workspace == nullptr || workspace_bytes < mas_b200_fused_workspace_bytes(B, D, T_x, T_y)) return MAS_ERR_WORKSPACE_TOO_SMALL;
+    // One launch: producer CTAs (FFMA contraction) and sweep CTAs run concurrently (mas_fused.cu).
+    if (!g_force_unfused) {
+        LogpParams lp{x_m, x_logs, z, nullptr, B, D, T_x, T_y};
+        const int rc1 = launch_fused(lp, x_len, y_len, path, durations, frame_token, workspace, workspace_bytes, max_neg_val,
+                                     static_cast<cudaStream_t>(stream));
+        if (rc1 != MAS_ERR_UNSUPPORTED_SHAPE) return rc1;
+    }
+    // Shapes the single launch does not take (frame count not a multiple of 4, > 80 channels, > 1024
+    // tokens): the same two programs back to back, scores staged in the workspace.
     float *logp = static_cast<float *>(workspace);
     int rc = mas_b200_logp_f32(x_m, x_logs, z, logp, B, D, T_x, T_y, stream);
     if (rc != MAS_OK) return rc;

@@ -1,0 +1,201 @@
+// mas_fused.cu -- kernel (2): log-likelihood + alignment search in ONE launch (models.py:362-382).
+//
+// Two kinds of CTAs share the grid and run concurrently:
+//   * producers (blockIdx < n_gemm): the FFMA contraction of mas_logp_cta.cuh for one tile of tokens
+//     of one utterance, walking 64-frame chunks in an interleaved order (producer j of n takes
+//     chunks j, j+n, j+2n, ...) so that the scores of EARLY frames of every utterance exist first;
+//     after each chunk is stored they raise that chunk's ready flag (fence + red.release.gpu);
+//   * one sweep CTA per utterance: kernel (1)'s program (mas_dp_cta.cuh) whose TMA box loads wait
+//     for the flag of the chunk they read (ld.acquire.gpu + fence.proxy.async), so the systolic
+//     sweep trails the producers by a few blocks instead of starting after the last FFMA.
+// Producers never wait for anybody and carry the lower block indices, so the launch cannot
+// deadlock whatever the residency; with both programs under half an SM's shared memory two CTAs
+// share an SM and the whole grid is resident for the training shapes.
+//
+// The scores travel through a [B,T_x,T_y] fp32 scratch in the caller's workspace, written once and
+// read once while still in the 126 MB L2 (25.6 MB for B=32, 200x1000).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "mas_dp_cta.cuh"
+#include "mas_logp_cta.cuh"
+
+namespace mas {
+namespace fused {
+
+constexpr int kThreads = 160;          // 4 sweep warps + filler | up to 20 token groups x 8 frame groups
+
+struct Geometry {
+    int n_gemm;        // producer CTAs = B * row_tiles * n_per
+    int row_tiles, tile_rows, n_per, nchunks;
+    int *ready;        // [B][nchunks]
+};
+
+template <int R, bool kDbg>
+__global__ void __launch_bounds__(kThreads, 2)
+mas_fused_kernel(const __grid_constant__ CUtensorMap tmap, PathParams pp, systolic::Plan plan, LogpParams lp, Geometry g) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((int)blockIdx.x < g.n_gemm) {
+        const int j = blockIdx.x % g.n_per, t = blockIdx.x / g.n_per;
+        const int rt = t % g.row_tiles, b = t / g.row_tiles;
+        const int count = (g.nchunks - j + g.n_per - 1) / g.n_per;
+        // profiling: producers stamp globaltimer per chunk behind the sweep CTAs' [B][16][16] block
+        long long *dbg_ns = (kDbg && pp.dbg_cycles) ? pp.dbg_cycles + ((size_t)pp.B * 16 + blockIdx.x) * 16 : nullptr;
+        logp::logp_cta<true>(lp, reinterpret_cast<float *>(smem), g.tile_rows, b, rt * g.tile_rows, j, g.n_per, count,
+                             g.ready + (size_t)b * g.nchunks, dbg_ns);
+    } else {
+        const int b = blockIdx.x - g.n_gemm;
+        systolic::dp_cta<R, kDbg, false, true>(tmap, pp, plan, smem, b, b, g.ready + (size_t)b * g.nchunks, g.row_tiles);
+    }
+}
+
+template <int R>
+static int launch_r(const CUtensorMap &tmap, const PathParams &pp, const systolic::Plan &plan, const LogpParams &lp,
+                    const Geometry &g, int smem_bytes, cudaStream_t stream) {
+    static int configured[64] = {0};
+    int dev = 0;
+    MAS_CUDA_TRY(cudaGetDevice(&dev));
+    if (pp.dbg_cycles != nullptr) {
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        mas_fused_kernel<R, true><<<g.n_gemm + pp.B, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
+        MAS_CUDA_TRY(cudaGetLastError());
+        return MAS_OK;
+    }
+    if (smem_bytes > configured[dev & 63]) {
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        configured[dev & 63] = smem_bytes;
+    }
+    if (getenv("MAS_B200_DEBUG") != nullptr) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mas_fused_kernel<R, false>, kThreads, smem_bytes);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, mas_fused_kernel<R, false>);
+        fprintf(stderr, "[mas_b200] fused kernel: %d CTAs/SM resident, %d regs, %zu B static smem\n", nb, fa.numRegs, fa.sharedSizeBytes);
+    }
+    mas_fused_kernel<R, false><<<g.n_gemm + pp.B, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
+    MAS_CUDA_TRY(cudaGetLastError());
+    return MAS_OK;
+}
+
+}  // namespace fused
+
+static size_t fused_flag_bytes(int B, int T_y) { return align_up((size_t)B * ceil_div(T_y, kGemmFrames) * 4, 256); }
+
+size_t fused_workspace_bytes(int B, int D, int T_x, int T_y) {
+    (void)D;
+    return align_up((size_t)B * T_x * T_y * 4, 256) + fused_flag_bytes(B, T_y) + path_systolic_workspace_bytes(B, T_x, T_y);
+}
+
+// MAS_OK: launched.  MAS_ERR_UNSUPPORTED_SHAPE: not for the single-launch path (the caller runs the two
+// kernels back to back instead).
+int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y_len, float *path, int32_t *durations,
+                 int32_t *frame_token, void *workspace, size_t workspace_bytes, float max_neg_val, cudaStream_t stream) {
+    using namespace fused;
+    static const bool debug = getenv("MAS_B200_DEBUG") != nullptr;
+#define MAS_FUSED_NO(why) do { if (debug) fprintf(stderr, "[mas_b200] single launch not taken: %s\n", why); return MAS_ERR_UNSUPPORTED_SHAPE; } while (0)
+    const int B = lp_in.B, D = lp_in.D, T_x = lp_in.T_x, T_y = lp_in.T_y;
+    if (B == 0) return MAS_OK;
+    if ((T_y & 3) || T_y < systolic::kBlk || D > logp::kPanel || D < 1 ||
+        (reinterpret_cast<uintptr_t>(lp_in.z) & 15) || (reinterpret_cast<uintptr_t>(path) & 15))
+        MAS_FUSED_NO("alignment / frame count / channel count");
+    int R, W;
+    if (!systolic::choose_shape(T_x, R, W) || W > 4) MAS_FUSED_NO("more than 4 sweep warps");
+    PFN_cuTensorMapEncodeTiled_v12000 encode = systolic::get_encode_fn();
+    if (encode == nullptr) MAS_FUSED_NO("no cuTensorMapEncodeTiled");
+    if (workspace == nullptr || workspace_bytes < fused_workspace_bytes(B, D, T_x, T_y)) return MAS_ERR_WORKSPACE_TOO_SMALL;
+
+    static int max_smem_cached[64] = {0}, num_sms_cached[64] = {0};
+    int dev = 0;
+    MAS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return MAS_ERR_INVALID_ARGUMENT;
+    if (max_smem_cached[dev] == 0) {
+        MAS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem_cached[dev], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        MAS_CUDA_TRY(cudaDeviceGetAttribute(&num_sms_cached[dev], cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int max_smem = max_smem_cached[dev] - 2048;
+    const int half_smem = (max_smem_cached[dev] + 1024) / 2 - 2048;   // two CTAs per SM (1 KB reserved per CTA)
+
+    // producers: token tiles of at most 160 tokens (20 groups of 8 -> 160 threads)
+    Geometry g{};
+    g.row_tiles = ceil_div(T_x, 160);
+    g.tile_rows = ceil_div(ceil_div(T_x, g.row_tiles), 8) * 8;
+    g.nchunks = ceil_div(T_y, kGemmFrames);
+    const int gemm_smem = logp::cta_smem_floats(D, g.tile_rows) * 4;
+
+    // sweep CTAs: K = 1, deepest ring that still lets two CTAs share an SM, else one per SM
+    systolic::Plan plan{};
+    bool ok = false, two_per_sm = false;
+    for (int pass = 0; pass < 2 && !ok; ++pass) {
+        const int budget = pass == 0 ? half_smem : max_smem;
+        if (gemm_smem > budget) continue;
+        for (int bits_smem = 1; bits_smem >= 0 && !ok; --bits_smem)
+            for (int S = 4; S >= 2 && !ok; --S) {
+                plan = systolic::make_plan(R, W, S, 1, T_y, bits_smem != 0, 8192);
+                if (plan.total <= budget) {
+                    ok = true;
+                    two_per_sm = pass == 0;
+                }
+            }
+    }
+    if (!ok) MAS_FUSED_NO("shared memory");
+    const int smem_bytes = gemm_smem > plan.total ? gemm_smem : plan.total;
+    const int64_t slots = (int64_t)num_sms_cached[dev] * (two_per_sm ? 2 : 1);
+    int64_t n_per = (slots - B) / ((int64_t)B * g.row_tiles);
+    if (n_per < 1) n_per = 1;
+    if (n_per > g.nchunks) n_per = g.nchunks;
+    g.n_per = (int)n_per;
+    g.n_gemm = B * g.row_tiles * g.n_per;
+
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    float *scores = reinterpret_cast<float *>(ws);
+    ws += align_up((size_t)B * T_x * T_y * 4, 256);
+    g.ready = reinterpret_cast<int *>(ws);
+    ws += fused_flag_bytes(B, T_y);
+    MAS_CUDA_TRY(cudaMemsetAsync(g.ready, 0, (size_t)B * g.nchunks * 4, stream));
+
+    LogpParams lp = lp_in;
+    lp.logp = scores;
+    PathParams pp{};
+    pp.value = scores;
+    pp.value_stride_b = (int64_t)T_x * T_y;
+    pp.value_stride_x = T_y;
+    pp.t_x = x_len;
+    pp.t_y = y_len;
+    pp.path = path;
+    pp.durations = durations;
+    pp.frame_token = frame_token;
+    pp.ws_bits = plan.bits_in_smem ? nullptr : reinterpret_cast<uint32_t *>(ws);
+    pp.B = B;
+    pp.T_x = T_x;
+    pp.T_y = T_y;
+    pp.max_neg_val = max_neg_val;
+    pp.dbg_cycles = g_dbg_cycles;
+
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {(cuuint64_t)T_y, (cuuint64_t)T_x, (cuuint64_t)B};
+    const cuuint64_t gstride[2] = {(cuuint64_t)T_y * 4, (cuuint64_t)T_x * T_y * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)systolic::kBlk, (cuuint32_t)(systolic::kBlk * plan.R), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, scores, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) MAS_FUSED_NO("tensor map encode failed");
+    if (debug)
+        fprintf(stderr, "[mas_b200] single launch: %d producers (%d per tile, %d tiles of %d tokens) + %d sweep CTAs, %d B smem, R=%d W=%d S=%d\n",
+                g.n_gemm, g.n_per, g.row_tiles, g.tile_rows, B, smem_bytes, plan.R, plan.W, plan.S);
+
+    switch (plan.R) {
+        case 1: return launch_r<1>(tmap, pp, plan, lp, g, smem_bytes, stream);
+        case 2: return launch_r<2>(tmap, pp, plan, lp, g, smem_bytes, stream);
+        case 3: return launch_r<3>(tmap, pp, plan, lp, g, smem_bytes, stream);
+        case 4: return launch_r<4>(tmap, pp, plan, lp, g, smem_bytes, stream);
+        case 5: return launch_r<5>(tmap, pp, plan, lp, g, smem_bytes, stream);
+        case 6: return launch_r<6>(tmap, pp, plan, lp, g, smem_bytes, stream);
+        case 8: return launch_r<8>(tmap, pp, plan, lp, g, smem_bytes, stream);
+        default: return MAS_ERR_UNSUPPORTED_SHAPE;
+    }
+}
+
+}  // namespace mas

@@ -42,4 +42,9 @@ extern long long *g_dbg_cycles;
 
 int launch_logp(const LogpParams &p, cudaStream_t stream);
 
+// single-launch logp + alignment search (mas_fused.cu); MAS_ERR_UNSUPPORTED_SHAPE -> run the two kernels
+size_t fused_workspace_bytes(int B, int D, int T_x, int T_y);
+int launch_fused(const LogpParams &lp, const int32_t *x_len, const int32_t *y_len, float *path, int32_t *durations,
+                 int32_t *frame_token, void *workspace, size_t workspace_bytes, float max_neg_val, cudaStream_t stream);
+
 }  // namespace mas

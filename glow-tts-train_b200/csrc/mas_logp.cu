@@ -8,15 +8,12 @@
 // chunk, and every thread contracts an 8 x 8 block of cells in registers (mas_logp_tile.cuh).
 // The arithmetic (operands, FFMA order, final adds) is the one the fused kernel uses, so both
 // produce bit-identical scores.
-#include "mas_kernels.cuh"
-#include "mas_logp_tile.cuh"
-#include "mas_ptx.cuh"
+#include "mas_logp_cta.cuh"
 
 namespace mas {
 namespace logp {
 
 constexpr int kMaxTileRows = 208;   // 26 row groups of 8 -> 208 threads
-constexpr int kPanel = 80;          // channels resident in shared memory at a time
 
 struct Geometry {
     int tile_rows;      // multiple of 8
@@ -105,15 +102,6 @@ __global__ void __launch_bounds__(256, 1) mas_logp_kernel(LogpParams p, Geometry
             }
         }
     };
-    auto stage_frames_async = [&](int ch, int buf) {
-        const int y0 = ch * kGemmFrames;
-        float *dst = sZ + buf * panel * kGemmFrames;
-        for (int i = tid; i < D * (kGemmFrames / 4); i += nthr) {
-            const int d = i >> 4, y = y0 + ((i & 15) << 2);
-            ptx::cp_async_16(dst + (i << 2), zg + (int64_t)d * T_y + (y < T_y ? y : 0), y < T_y);
-        }
-        ptx::cp_async_commit();
-    };
     auto store_tile = [&](int y0, float (&acc)[8][8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -143,27 +131,11 @@ __global__ void __launch_bounds__(256, 1) mas_logp_kernel(LogpParams p, Geometry
 
     const int chunk0 = blockIdx.x * g.chunks_per_cta;
     const int chunk1 = min(chunk0 + g.chunks_per_cta, g.nchunks);
-    float acc[8][8];
-    if (async_z) {
-        stage_frames_async(chunk0, 0);                  // in flight while the token side is prepared
-        stage_tokens(0, 0, D, true);
-        for (int ch = chunk0; ch < chunk1; ++ch) {
-            const int buf = (ch - chunk0) & 1;
-            if (ch + 1 < chunk1) {
-                stage_frames_async(ch + 1, buf ^ 1);    // buffer buf^1 was released by the barrier below
-                ptx::cp_async_wait<1>();
-            } else {
-                ptx::cp_async_wait<0>();
-            }
-            __syncthreads();                            // chunk ch (and the token side) visible to everyone
-            if (worker) {
-                gemm_tile_8x8<true>(sInv, sMiv, sZ + buf * panel * kGemmFrames, D, tile_rows, rg, cg, acc);
-                store_tile(ch * kGemmFrames, acc);
-            }
-            __syncthreads();                            // everyone is done reading buffer buf
-        }
+    if (async_z && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+        logp_cta<false>(p, sm, tile_rows, b, x0, chunk0, 1, chunk1 - chunk0, nullptr);
         return;
     }
+    float acc[8][8];
     // generic path: any alignment, any channel count (panels of 80)
     for (int ch = chunk0; ch < chunk1; ++ch) {
         const int y0 = ch * kGemmFrames;

@@ -178,6 +178,24 @@ __device__ __forceinline__ int ld_acquire_cluster_shared(const int *p) {
     return v;
 }
 
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ---- flags in global memory (producer CTAs -> consumer CTAs of the same launch) --------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int *p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy writes (any state space) ordered before subsequent async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ---- streaming (evict-first) 16-byte global store ---------------------------------------------
 __device__ __forceinline__ void st_global_cs_v4(float4 *p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

@@ -60,6 +60,9 @@ void mas_b200_debug_set_cycle_buffer(void *device_buffer);
 /* Testing hook: force the number of CTAs (thread-block cluster size: 1, 2, 4, 8) that share one
  * utterance in kernel (1); 0 restores the heuristic. */
 void mas_b200_debug_force_cluster(int ctas_per_utterance);
+/* Testing hook: non-zero makes mas_b200_fused_maximum_path_f32 run its two programs as two launches
+ * (the path it takes anyway for shapes the single launch does not support). */
+void mas_b200_debug_force_unfused(int on);
 /* MAS_OK iff the current CUDA device can run the kernels (compute capability 10.x). */
 int mas_b200_device_ok(void);
 
@@ -117,8 +120,9 @@ int mas_b200_logp_f32(const float *x_m, const float *x_logs, const float *z, flo
                       int B, int D, int T_x, int T_y, mas_stream_t stream);
 
 /*
- * Kernel (2): fused log-likelihood + alignment search; the [B,T_x,T_y] score matrix is never
- * written to memory.  Replaces models.py:362-382 (+ :393 through `durations`).
+ * Kernel (2): log-likelihood + alignment search in one launch: producer CTAs contract the scores in
+ * 64-frame chunks, sweep CTAs consume them as they appear (ready flags), through an L2-resident
+ * scratch in the workspace.  Replaces models.py:362-382 (+ :393 through `durations`).
  *   x_len, y_len int32 [B] device: valid tokens / frames (what the prefix masks encode).
  * Other arguments as above.  logp tiles are accurate to 1e-5 relative against the fp64 formula;
  * the path equals kernel (1) run on mas_b200_logp_f32's output bit for bit.

@@ -98,3 +98,27 @@ def test_fused_is_length_robust(pkg, oracle):
         z[b, :, t_y[b]:] = -1e3
     c = pkg.fused_maximum_path(to_dev(x_m), to_dev(x_logs), to_dev(z), torch.from_numpy(t_x), torch.from_numpy(t_y))[0]
     assert torch.equal(a, c)
+
+
+@pytest.mark.parametrize("shape", [(4, 80, 200, 1000), (3, 80, 64, 256), (2, 40, 300, 640), (40, 80, 96, 320)])
+def test_single_launch_equals_two_launches(pkg, oracle, shape):
+    """The single-launch producer/consumer kernel and the two kernels back to back run the same two
+    programs: identical path, durations and frame->token map, bit for bit."""
+    lib = pkg._lib.load()
+    B, D, T_x, T_y = shape
+    rng = np.random.default_rng(zlib.crc32(repr(shape).encode()))
+    t_x, t_y = ragged_lengths(rng, B, T_x, T_y)
+    x_m, x_logs, z = synth_prior(rng, B, D, T_x, T_y, t_x, t_y, False)
+    args = (to_dev(x_m), to_dev(x_logs), to_dev(z), torch.from_numpy(t_x), torch.from_numpy(t_y))
+    one = pkg.fused_maximum_path(*args, want_frame_token=True)
+    torch.cuda.synchronize()
+    lib.mas_b200_debug_force_unfused(1)
+    try:
+        two = pkg.fused_maximum_path(*args, want_frame_token=True)
+        torch.cuda.synchronize()
+    finally:
+        lib.mas_b200_debug_force_unfused(0)
+    for a, b in zip(one, two):
+        assert torch.equal(a, b)
+    logp = pkg.log_likelihood_matrix(*args[:3]).cpu().numpy()
+    assert np.array_equal(one[0].cpu().numpy().astype(np.int32), oracle.maximum_path(logp, t_x, t_y))
