@@ -67,8 +67,10 @@ __device__ __forceinline__ void spin_fail() { __trap(); }
 // scores (acquire at GPU scope), then order those generic-proxy writes before our TMA read.
 __device__ __forceinline__ void wait_chunk_ready(const int *ready, int chunk, int target) {
     uint32_t spins = 0;
-    while (ptx::ld_acquire_gpu(ready + chunk) < target)
+    while (ptx::ld_acquire_gpu(ready + chunk) < target) {
+        __nanosleep(256);                               // the producers may share this SM: do not burn issue slots
         if (++spins > kSpinLimit) spin_fail();
+    }
     ptx::fence_proxy_async_all();
 }
 
@@ -400,6 +402,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                 const long long t0 = kDbg ? clock64() : 0;
                 while (seen_prev <= cb) {                       // previous warp has published block cb
                     seen_prev = prev_remote ? ptx::ld_acquire_cluster_shared(&done[warp]) : ptx::ld_acquire_shared(&done[warp]);
+                    if (kFused && seen_prev <= cb) __nanosleep(128);   // a producer CTA may share this SM
                     if (++spins > kSpinLimit) spin_fail();
                 }
                 while (seen_next + kBndBlocks <= cb) {          // next warp has consumed block cb - ring depth

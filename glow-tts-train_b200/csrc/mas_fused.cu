@@ -26,12 +26,13 @@
 namespace mas {
 namespace fused {
 
-constexpr int kThreads = 160;          // 4 sweep warps + filler | up to 20 token groups x 8 frame groups
+constexpr int kThreads = 224;          // producers: 28 token groups of 4 x 8 frame groups | sweep CTAs use 160 of them
 
 struct Geometry {
     int n_gemm;        // producer CTAs = B * row_tiles * n_per
     int row_tiles, tile_rows, n_per, nchunks;
-    int *ready;        // [B][nchunks]
+    int *ready;        // [B][nchunks] chunk ready counters
+    int *queue;        // [B][row_tiles] next chunk to contract, per token tile
 };
 
 template <int R, bool kDbg>
@@ -39,6 +40,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 mas_fused_kernel(const __grid_constant__ CUtensorMap tmap, PathParams pp, systolic::Plan plan, LogpParams lp, Geometry g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     if ((int)blockIdx.x < g.n_gemm) {
+        // producer j of the n that share a token tile takes chunks j, j+n, j+2n, ...  (a shared chunk
+        // queue and dealing the producers out across SMs were tried: no better)
         const int j = blockIdx.x % g.n_per, t = blockIdx.x / g.n_per;
         const int rt = t % g.row_tiles, b = t / g.row_tiles;
         const int count = (g.nchunks - j + g.n_per - 1) / g.n_per;
@@ -82,7 +85,9 @@ static int launch_r(const CUtensorMap &tmap, const PathParams &pp, const systoli
 
 }  // namespace fused
 
-static size_t fused_flag_bytes(int B, int T_y) { return align_up((size_t)B * ceil_div(T_y, kGemmFrames) * 4, 256); }
+static size_t fused_flag_bytes(int B, int T_y) {      // ready counters + per-tile chunk queues (<= 32 tiles per utterance)
+    return align_up((size_t)B * (ceil_div(T_y, kGemmFrames) + 32) * 4, 256);
+}
 
 size_t fused_workspace_bytes(int B, int D, int T_x, int T_y) {
     (void)D;
@@ -118,9 +123,9 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
     const int max_smem = max_smem_cached[dev] - 2048;
     const int half_smem = (max_smem_cached[dev] + 1024) / 2 - 2048;   // two CTAs per SM (1 KB reserved per CTA)
 
-    // producers: token tiles of at most 160 tokens (20 groups of 8 -> 160 threads)
+    // producers: token tiles of at most 112 tokens (28 groups of 4 -> 224 threads)
     Geometry g{};
-    g.row_tiles = ceil_div(T_x, 160);
+    g.row_tiles = ceil_div(T_x, 112);
     g.tile_rows = ceil_div(ceil_div(T_x, g.row_tiles), 8) * 8;
     g.nchunks = ceil_div(T_y, kGemmFrames);
     const int gemm_smem = logp::cta_smem_floats(D, g.tile_rows) * 4;
@@ -153,8 +158,9 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
     float *scores = reinterpret_cast<float *>(ws);
     ws += align_up((size_t)B * T_x * T_y * 4, 256);
     g.ready = reinterpret_cast<int *>(ws);
+    g.queue = g.ready + (size_t)B * g.nchunks;
     ws += fused_flag_bytes(B, T_y);
-    MAS_CUDA_TRY(cudaMemsetAsync(g.ready, 0, (size_t)B * g.nchunks * 4, stream));
+    MAS_CUDA_TRY(cudaMemsetAsync(g.ready, 0, (size_t)B * (g.nchunks + g.row_tiles) * 4, stream));
 
     LogpParams lp = lp_in;
     lp.logp = scores;

@@ -13,7 +13,7 @@
 namespace mas {
 namespace logp {
 
-constexpr int kMaxTileRows = 208;   // 26 row groups of 8 -> 208 threads
+constexpr int kMaxTileRows = 112;   // 28 token groups of 4 x 8 frame groups -> 224 threads; two CTAs share an SM
 
 struct Geometry {
     int tile_rows;      // multiple of 8
@@ -29,7 +29,7 @@ struct Geometry {
 static Geometry make_geometry(int B, int D, int T_x, int T_y, int num_sms) {
     Geometry g;
     g.row_tiles = ceil_div(T_x, kMaxTileRows);
-    g.tile_rows = ceil_div(ceil_div(T_x, g.row_tiles), 8) * 8;
+    g.tile_rows = ceil_div(ceil_div(T_x, g.row_tiles), 8) * 8;   // multiple of 8: 32-byte aligned operand rows
     g.nchunks = ceil_div(T_y, kGemmFrames);
     // CTAs along the frame axis: fewest (waves x chunks per CTA), counting ~0.7 chunk of token-side
     // staging per CTA
@@ -38,21 +38,21 @@ static Geometry make_geometry(int B, int D, int T_x, int T_y, int num_sms) {
     g.chunks_per_cta = g.nchunks;
     for (int cpc = 1; cpc <= g.nchunks; ++cpc) {
         const int64_t ctas = base * ceil_div(g.nchunks, cpc);
-        const double cost = (double)((ctas + num_sms - 1) / num_sms) * (cpc + 0.7);
+        const double cost = (double)((ctas + 2 * num_sms - 1) / (2 * num_sms)) * (cpc + 0.7);   // two CTAs per SM
         if (cost < best - 1e-9) {
             best = cost;
             g.chunks_per_cta = cpc;
         }
     }
     g.splits = ceil_div(g.nchunks, g.chunks_per_cta);
-    g.threads = max(64, ceil_div(g.tile_rows, 32) * 32);
+    g.threads = max(64, ceil_div(g.tile_rows / kGemmTM * 8, 32) * 32);
     g.panel = D < kPanel ? D : kPanel;
     g.smem_bytes = (2 * g.panel * g.tile_rows + 2 * g.panel * kGemmFrames + 2 * g.tile_rows) * 4;
     return g;
 }
 
 // grid: (splits, row_tiles, B)
-__global__ void __launch_bounds__(256, 1) mas_logp_kernel(LogpParams p, Geometry g) {
+__global__ void __launch_bounds__(224, 2) mas_logp_kernel(LogpParams p, Geometry g) {
     extern __shared__ __align__(16) float sm[];
     const int tile_rows = g.tile_rows, panel = g.panel;
     float *sInv = sm;                                   // [panel][tile_rows]
@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(256, 1) mas_logp_kernel(LogpParams p, Geometry
     const float *zg = p.z + (int64_t)b * D * T_y;
     float *out = p.logp + (int64_t)b * T_x * T_y;
 
-    const int rg = tid >> 3, cg = tid & 7;              // 8 tokens x {4+4} frames per thread
-    const bool worker = rg * 8 < tile_rows;
+    const int rg = tid >> 3, cg = tid & 7;              // kGemmTM tokens x {4+4} frames per thread
+    const bool worker = rg * kGemmTM < tile_rows;
     const bool vec_ok = ((T_y & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const int npanels = ceil_div(D, panel);
     // frames staged by cp.async (16 bytes, no registers, overlapped with the previous chunk's FFMAs)
@@ -102,10 +102,10 @@ __global__ void __launch_bounds__(256, 1) mas_logp_kernel(LogpParams p, Geometry
             }
         }
     };
-    auto store_tile = [&](int y0, float (&acc)[8][8]) {
+    auto store_tile = [&](int y0, float (&acc)[kGemmTM][8]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int xr = rg * 8 + i, x = x0 + xr;
+        for (int i = 0; i < kGemmTM; ++i) {
+            const int xr = rg * kGemmTM + i, x = x0 + xr;
             if (x >= T_x) break;
             const float l1 = sL1[xr], l4 = sL4[xr];
             float *row = out + (int64_t)x * T_y;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256, 1) mas_logp_kernel(LogpParams p, Geometry
         logp_cta<false>(p, sm, tile_rows, b, x0, chunk0, 1, chunk1 - chunk0, nullptr);
         return;
     }
-    float acc[8][8];
+    float acc[kGemmTM][8];
     // generic path: any alignment, any channel count (panels of 80)
     for (int ch = chunk0; ch < chunk1; ++ch) {
         const int y0 = ch * kGemmFrames;
@@ -151,9 +151,9 @@ __global__ void __launch_bounds__(256, 1) mas_logp_kernel(LogpParams p, Geometry
             __syncthreads();
             if (worker) {
                 if (pn == 0)
-                    gemm_tile_8x8<true>(sInv, sMiv, sZ, dn, tile_rows, rg, cg, acc);
+                    gemm_tile<kGemmTM, true>(sInv, sMiv, sZ, dn, tile_rows, rg, cg, acc);
                 else
-                    gemm_tile_8x8<false>(sInv, sMiv, sZ, dn, tile_rows, rg, cg, acc);
+                    gemm_tile<kGemmTM, false>(sInv, sMiv, sZ, dn, tile_rows, rg, cg, acc);
             }
         }
         if (worker) store_tile(y0, acc);

@@ -21,7 +21,8 @@ __host__ __device__ inline int cta_smem_floats(int D, int tile_rows) {
 // chunks chunk_first, chunk_first + chunk_stride, ... (chunk_count of them, < nchunks)
 template <bool kSignal>
 __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int tile_rows, int b, int x0, int chunk_first,
-                                         int chunk_stride, int chunk_count, int *ready, long long *dbg_ns = nullptr) {
+                                         int chunk_stride, int chunk_count, int *ready, long long *dbg_ns = nullptr,
+                                         int *queue = nullptr, int nchunks = 0) {
     const int D = p.D, T_x = p.T_x, T_y = p.T_y;
     float *sInv = sm;                                   // [D][tile_rows]
     float *sMiv = sInv + D * tile_rows;                 // [D][tile_rows]
@@ -34,8 +35,8 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
     const float *xl = p.x_logs ? p.x_logs + (int64_t)b * D * T_x : nullptr;
     const float *zg = p.z + (int64_t)b * D * T_y;
     float *out = p.logp + (int64_t)b * T_x * T_y;
-    const int rg = tid >> 3, cg = tid & 7;              // 8 tokens x {4+4} frames per thread
-    const bool worker = rg * 8 < tile_rows;
+    const int rg = tid >> 3, cg = tid & 7;              // kGemmTM tokens x {4+4} frames per thread
+    const bool worker = rg * kGemmTM < tile_rows;
 
     auto stage_frames_async = [&](int ch, int buf) {
         const int y0 = ch * kGemmFrames;
@@ -47,9 +48,25 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
         ptx::cp_async_commit();
     };
 
-    if (chunk_count <= 0) return;
+    // Chunk order: a fixed arithmetic sequence, or (queue != null) whatever this tile's shared counter
+    // hands out next -- CTAs that share their SM with a sweep CTA then simply take fewer chunks.
+    __shared__ int s_next;
+    auto take = [&]() -> int {                          // every thread gets the same answer
+        __syncthreads();
+        if (tid == 0) s_next = atomicAdd(queue, 1);
+        __syncthreads();
+        return s_next;
+    };
+    int ch = chunk_first, ch_next = 0;
+    if (queue != nullptr) {
+        ch = take();
+        if (ch >= nchunks) return;
+        chunk_count = nchunks;                          // upper bound; the loop ends when the queue is dry
+    } else if (chunk_count <= 0) {
+        return;
+    }
     if (dbg_ns && tid == 0) dbg_ns[0] = ptx::globaltimer_ns();
-    stage_frames_async(chunk_first, 0);                 // in flight while the token side is prepared
+    stage_frames_async(ch, 0);                          // in flight while the token side is prepared
     // token side: thread x stages token x0+x for every channel (coalesced over x, eight loads in
     // flight) and sums its row constants on the way, channels ascending
     for (int x = tid; x < tile_rows; x += nthr) {
@@ -72,22 +89,30 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
         sL1[x] = l1;
         sL4[x] = l4;
     }
-    float acc[8][8];
+    float acc[kGemmTM][8];
     for (int k = 0; k < chunk_count; ++k) {
-        const int ch = chunk_first + k * chunk_stride, buf = k & 1;
-        if (k + 1 < chunk_count) {
-            stage_frames_async(ch + chunk_stride, buf ^ 1);     // buffer buf^1 was released by the barrier below
+        const int buf = k & 1;
+        bool more;
+        if (queue != nullptr) {
+            ch_next = take();
+            more = ch_next < nchunks;
+        } else {
+            ch_next = ch + chunk_stride;
+            more = k + 1 < chunk_count;
+        }
+        if (more) {
+            stage_frames_async(ch_next, buf ^ 1);       // buffer buf^1 was released by the barrier below
             ptx::cp_async_wait<1>();
         } else {
             ptx::cp_async_wait<0>();
         }
         __syncthreads();                                // chunk ch (and the token side) visible to everyone
         if (worker) {
-            gemm_tile_8x8<true>(sInv, sMiv, sZ + buf * D * kGemmFrames, D, tile_rows, rg, cg, acc);
+            gemm_tile<kGemmTM, true>(sInv, sMiv, sZ + buf * D * kGemmFrames, D, tile_rows, rg, cg, acc);
             const int y0 = ch * kGemmFrames;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int xr = rg * 8 + i, x = x0 + xr;
+            for (int i = 0; i < kGemmTM; ++i) {
+                const int xr = rg * kGemmTM + i, x = x0 + xr;
                 if (x >= T_x) break;
                 const float l1 = sL1[xr], l4 = sL4[xr];
                 float *row = out + (int64_t)x * T_y;
@@ -111,6 +136,8 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
             ptx::red_release_gpu_add(ready + ch, 1);
             if (dbg_ns) dbg_ns[k < 15 ? k + 1 : 15] = ptx::globaltimer_ns();
         }
+        if (!more) break;
+        ch = ch_next;
     }
 }
 

@@ -69,56 +69,73 @@ __device__ __forceinline__ void logp_cell_fma(float &c, float inv_var, float mea
 __device__ __forceinline__ float logp_cell_finish(float l1, float c, float l4) { return (l1 + c) + l4; }
 
 // ---------------------------------------------------------------------------------------------
-// Register-tiled contraction: every thread owns an 8 (tokens) x 8 (frames) block of cells.
+// Register-tiled contraction: every thread owns a TM (tokens) x 8 (frames) block of cells.
 // Shared-memory operands:
 //   sInv, sMiv : [D][tile_rows]   token-side, token index contiguous
 //   sZ         : [D][64]          frame-side, a 64-frame chunk of z; -0.5 z^2 is formed in registers
-// Thread (rg, cg): tokens 8 rg .. 8 rg + 7; frames {4 cg .. 4 cg + 3} and {32 + 4 cg .. 32 + 4 cg + 3},
+// Thread (rg, cg): tokens TM rg .. TM rg + TM-1; frames {4 cg .. 4 cg + 3} and {32 + 4 cg .. 32 + 4 cg + 3},
 // so that the 8 column groups of a warp read one contiguous 128-byte line per LDS.128.
-// Per channel: 6 LDS.128 + 8 FMUL feed 128 FFMA -- the shared-memory port (32 floats/cycle into
-// registers per SM) is what bounds a CUDA-core contraction, so as few operand floats as possible.
+// Measured on B200 (profiles/probes/probe_ffma2.cu, FFMA per cycle per SM of 128):
+//   8x8 tiles, 208 tokens, 224 threads, 1 CTA/SM : 68      4x8 tiles, 104 tokens, 224 threads, 2 CTA/SM : 98
+// The smaller tile loads more operand floats per FFMA (0.31 vs 0.25) but leaves room for 14 warps per
+// SM, which hides the shared-memory latency and the register-bank conflicts nvcc leaves behind.
 // ---------------------------------------------------------------------------------------------
 constexpr int kGemmFrames = 64;   // frames per chunk
+constexpr int kGemmTM = 4;        // tokens per thread
 
-template <bool kInit>
-__device__ __forceinline__ void gemm_tile_8x8(const float *__restrict__ sInv, const float *__restrict__ sMiv,
-                                              const float *__restrict__ sZ, int D, int tile_rows, int rg, int cg,
-                                              float (&acc)[8][8]) {
+// kD: compile-time channel count (80 mel channels, the case that matters) or 0 = run-time D
+template <int TM, bool kInit, int kD>
+__device__ __forceinline__ void gemm_tile_d(const float *__restrict__ sInv, const float *__restrict__ sMiv,
+                                            const float *__restrict__ sZ, int D_rt, int tile_rows, int rg, int cg,
+                                            float (&acc)[TM][8]) {
+    const int D = kD ? kD : D_rt;
+    static_assert(TM % 4 == 0, "token tile is loaded with 16-byte reads");
     if (kInit) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     }
-    const float *pa = sInv + rg * 8, *pb = sMiv + rg * 8;
+    const float *pa = sInv + rg * TM, *pb = sMiv + rg * TM;
     const float *pz = sZ + cg * 4;
 #pragma unroll 2
     for (int d = 0; d < D; ++d) {
-        const float4 a0 = *reinterpret_cast<const float4 *>(pa), a1 = *reinterpret_cast<const float4 *>(pa + 4);
-        const float4 b0 = *reinterpret_cast<const float4 *>(pb), b1 = *reinterpret_cast<const float4 *>(pb + 4);
+        float av[TM], bv[TM];
+#pragma unroll
+        for (int q = 0; q < TM / 4; ++q) {
+            const float4 a = *reinterpret_cast<const float4 *>(pa + 4 * q), b = *reinterpret_cast<const float4 *>(pb + 4 * q);
+            av[4 * q] = a.x, av[4 * q + 1] = a.y, av[4 * q + 2] = a.z, av[4 * q + 3] = a.w;
+            bv[4 * q] = b.x, bv[4 * q + 1] = b.y, bv[4 * q + 2] = b.z, bv[4 * q + 3] = b.w;
+        }
         const float4 z0 = *reinterpret_cast<const float4 *>(pz), z1 = *reinterpret_cast<const float4 *>(pz + 32);
         pa += tile_rows;
         pb += tile_rows;
         pz += kGemmFrames;
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
         float qv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) qv[j] = -0.5f * (zv[j] * zv[j]);      // models.py:368
-        // Same per-cell order as logp_cell_fma (first the inv_var term, then the mean term), but
-        // issued as two sweeps over the register tile so that consecutive FFMAs share an operand
-        // (register reuse cache): three distinct register reads per FFMA would otherwise halve the
-        // issue rate on bank conflicts.
+        // Same per-cell order as logp_cell_fma (first the inv_var term, then the mean term), issued
+        // as two sweeps over the register tile so that consecutive FFMAs share an operand.
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], qv[j], acc[i][j]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(bv[i], zv[j], acc[i][j]);
     }
+}
+
+template <int TM, bool kInit>
+__device__ __forceinline__ void gemm_tile(const float *__restrict__ sInv, const float *__restrict__ sMiv,
+                                          const float *__restrict__ sZ, int D, int tile_rows, int rg, int cg,
+                                          float (&acc)[TM][8]) {
+    if (D == 80)
+        gemm_tile_d<TM, kInit, 80>(sInv, sMiv, sZ, D, tile_rows, rg, cg, acc);
+    else
+        gemm_tile_d<TM, kInit, 0>(sInv, sMiv, sZ, D, tile_rows, rg, cg, acc);
 }
 
 }  // namespace mas
