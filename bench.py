@@ -133,7 +133,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # the reference arm (CPU)
 # ----------------------------------------------------------------------------------------------
-def reference_setup(B, D, T_x, T_y):
+def reference_setup(B, D, T_x, T_y, mean_only=False):
     oracle = entry.load_oracle()
     core = oracle.reference_core("omp")
     kind = "reference"
@@ -146,7 +146,7 @@ def reference_setup(B, D, T_x, T_y):
     cores = oracle.host_threads()
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     torch.set_num_threads(cores)
-    x_m, x_logs, z, x_len, y_len = synth_inputs(B, D, T_x, T_y, SEED + 1)
+    x_m, x_logs, z, x_len, y_len = synth_inputs(B, D, T_x, T_y, SEED + 1, mean_only)   # zeros when mean_only, as models.py:139 does
     x_mask = (torch.arange(T_x)[None] < x_len[:, None]).float()
     z_mask = (torch.arange(T_y)[None] < y_len[:, None]).float()
     attn_mask = x_mask[:, :, None] * z_mask[:, None, :]              # models.py:337 (squeezed)
@@ -171,7 +171,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    step, kind, cores = reference_setup(B, D, T_x, T_y)
+    step, kind, cores = reference_setup(B, D, T_x, T_y, args.mean_only)
     sec = time_reference(step, args.steps, args.warmup)
     cells = B * T_x * T_y
     value = cells / sec
@@ -179,7 +179,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "lengths": "full", "host": "CPU only: torch logp program (models.py:363-376) "
+        "config": {"workload": desc, "lengths": "full", "mean_only": args.mean_only, "host": "CPU only: torch logp program (models.py:363-376) "
                    "+ monotonic_align.maximum_path around the reference's OpenMP Cython kernel"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{args.steps} full batches of the workload (B={B})"},
@@ -212,16 +212,21 @@ def run_ours(args):
     assert pkg._lib.load().mas_b200_device_ok() == 0, "device is not sm_100 (B200)"
     standalone = args.workload == "c1"
 
+    mean_only = args.mean_only          # x_logs == 0 (config.py:52 default): passed as None, not copied
+
+    def drop_logs(t):
+        return (t[0], None, t[2], t[3], t[4]) if mean_only else t
+
     cells = B * T_x * T_y
-    in_bytes = 4 * B * D * (T_y + 2 * T_x) + 8 * B
+    in_bytes = 4 * B * D * (T_y + (1 if mean_only else 2) * T_x) + 8 * B
     out_bytes = 4 * cells + 4 * B * T_x
     # ---- resident inputs, rotated so that consecutive steps never hit L2 ----
     per_set = in_bytes + out_bytes + pkg._lib.load().mas_b200_fused_workspace_bytes(B, D, T_x, T_y)
     n_sets = max(3, int(2.5 * L2_BYTES // per_set) + 1)
     sets = []
     for i in range(n_sets):
-        x_m, x_logs, z, x_len, y_len = synth_inputs(B, D, T_x, T_y, SEED + 1 + rank * 1000 + i)
-        sets.append(tuple(t.to(dev) for t in (x_m, x_logs, z, x_len, y_len)))
+        x_m, x_logs, z, x_len, y_len = synth_inputs(B, D, T_x, T_y, SEED + 1 + rank * 1000 + i, mean_only)
+        sets.append(drop_logs(tuple(t.to(dev) for t in (x_m, x_logs, z, x_len, y_len))))
     logp_sets = None
     if standalone:
         logp_sets = [(pkg.log_likelihood_matrix(s[0], s[1], s[2]), s[3], s[4]) for s in sets]
@@ -294,7 +299,8 @@ def run_ours(args):
     # two streams (double-buffered pinned results), the way a host loop that feeds the GPU would be
     # written: step i's D2H overlaps step i+1's H2D and kernels (separate copy engines).
     n_lanes = 3
-    host = [tuple(t.pin_memory() for t in synth_inputs(B, D, T_x, T_y, SEED + 77 + rank * 1000 + i)) for i in range(n_lanes)]
+    host = [drop_logs(tuple(t.pin_memory() for t in synth_inputs(B, D, T_x, T_y, SEED + 77 + rank * 1000 + i, mean_only)))
+            for i in range(n_lanes)]
     host_out = [torch.empty((B, T_x, T_y), dtype=torch.float32).pin_memory() for _ in range(n_lanes)]
     host_dur = [torch.empty((B, T_x), dtype=torch.int32).pin_memory() for _ in range(n_lanes)]
     lanes = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
@@ -311,7 +317,7 @@ def run_ours(args):
                 checksum[0] += int(host_dur[k][0, 0])
             with torch.cuda.stream(lanes[k]):
                 x_m, x_logs, z, x_len, y_len = host[k]
-                d = [t.to(dev, non_blocking=True) for t in (x_m, x_logs, z, x_len, y_len)]
+                d = [None if t is None else t.to(dev, non_blocking=True) for t in (x_m, x_logs, z, x_len, y_len)]
                 path, dur = pkg.fused_maximum_path(*d)
                 host_out[k].copy_(path, non_blocking=True)
                 host_dur[k].copy_(dur, non_blocking=True)
@@ -353,7 +359,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "per_gpu_batch": B, "global_batch": B * world, "lengths": "full",
-                       "channels": D, "parallelism": f"utterance-sharded x{world}, no collective",
+                       "channels": D, "mean_only": mean_only, "parallelism": f"utterance-sharded x{world}, no collective",
                        "l2": f"inputs/outputs rotated over {n_sets} buffer sets ({n_sets * per_set / 2**20:.0f} MiB > L2)",
                        "kernels_per_step": launches_per_step,
                        "launch": f"{args.steps} steps captured in one CUDA graph, one replay timed"},
@@ -368,7 +374,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
         }
         if world == 1 and not args.no_cpu_baseline:
-            ref_step, kind, cores = reference_setup(B, D, T_x, T_y)
+            ref_step, kind, cores = reference_setup(B, D, T_x, T_y, mean_only)
             ref_step()
             reps, t0 = 0, time.perf_counter()
             while reps < 3 or (time.perf_counter() - t0 < args.cpu_seconds and reps < 400):
@@ -384,7 +390,7 @@ def run_ours(args):
                 oracle = entry.load_oracle()
                 core = oracle.reference_core("omp")
                 kern = core.maximum_path_c if core is not None else None
-                xg = [t.to(dev) for t in synth_inputs(B, D, T_x, T_y, SEED + 5)]
+                xg = [t.to(dev) for t in synth_inputs(B, D, T_x, T_y, SEED + 5, mean_only)]
                 xmask = (torch.arange(T_x, device=dev)[None] < xg[3][:, None]).float()
                 zmask = (torch.arange(T_y, device=dev)[None] < xg[4][:, None]).float()
                 amask = xmask[:, :, None] * zmask[:, None, :]
@@ -419,6 +425,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mean-only", action="store_true",
+                    help="x_logs == 0 (the reference's default ModelConfig.mean_only): the contraction halves")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -47,7 +47,7 @@ static Geometry make_geometry(int B, int D, int T_x, int T_y, int num_sms) {
     g.splits = ceil_div(g.nchunks, g.chunks_per_cta);
     g.threads = max(64, ceil_div(g.tile_rows / kGemmTM * 8, 32) * 32);
     g.panel = D < kPanel ? D : kPanel;
-    g.smem_bytes = (2 * g.panel * g.tile_rows + 2 * g.panel * kGemmFrames + 2 * g.tile_rows) * 4;
+    g.smem_bytes = cta_smem_floats(g.panel, g.tile_rows) * 4;
     return g;
 }
 

@@ -15,7 +15,7 @@ constexpr int kPanel = 80;          // channels resident in shared memory at a t
 
 // floats of shared memory the program needs
 __host__ __device__ inline int cta_smem_floats(int D, int tile_rows) {
-    return 2 * D * tile_rows + 2 * D * kGemmFrames + 2 * tile_rows;
+    return 2 * D * tile_rows + 2 * D * kGemmFrames + 2 * tile_rows + kGemmFrames;
 }
 
 // chunks chunk_first, chunk_first + chunk_stride, ... (chunk_count of them, < nchunks)
@@ -29,6 +29,8 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
     float *sZ = sMiv + D * tile_rows;                   // [2][D][64]  (double-buffered chunk of z)
     float *sL1 = sZ + 2 * D * kGemmFrames;              // [tile_rows]
     float *sL4 = sL1 + tile_rows;                       // [tile_rows]
+    float *sL2 = sL4 + tile_rows;                       // [64] mean_only: per-frame sum of -0.5 z^2
+    const bool mean_only = p.x_logs == nullptr;         // config.py:52, the reference default
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const float *xm = p.x_m + (int64_t)b * D * T_x;
@@ -107,8 +109,25 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
             ptx::cp_async_wait<0>();
         }
         __syncthreads();                                // chunk ch (and the token side) visible to everyone
+        if (mean_only) {
+            // inv_var == 1: the inv_var term does not depend on the token (models.py:367-369 with
+            // x_logs == 0): one sum per frame, channels ascending
+            if (tid < kGemmFrames) {
+                const float *zc = sZ + buf * D * kGemmFrames + tid;
+                float l2 = 0.f;
+                for (int d = 0; d < D; ++d) {
+                    const float zv = zc[d * kGemmFrames];
+                    l2 = fmaf(-0.5f * zv, zv, l2);
+                }
+                sL2[tid] = l2;
+            }
+            __syncthreads();
+        }
         if (worker) {
-            gemm_tile<kGemmTM, true>(sInv, sMiv, sZ + buf * D * kGemmFrames, D, tile_rows, rg, cg, acc);
+            if (mean_only)
+                gemm_tile<kGemmTM, true, true>(sInv, sMiv, sZ + buf * D * kGemmFrames, D, tile_rows, rg, cg, acc);
+            else
+                gemm_tile<kGemmTM, true, false>(sInv, sMiv, sZ + buf * D * kGemmFrames, D, tile_rows, rg, cg, acc);
             const int y0 = ch * kGemmFrames;
 #pragma unroll
             for (int i = 0; i < kGemmTM; ++i) {
@@ -121,10 +140,18 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
                     const int y = y0 + 32 * h + 4 * cg;
                     if (y < T_y) {                      // T_y % 4 == 0: whole float4 or nothing
                         float4 r;
-                        r.x = logp_cell_finish(l1, acc[i][4 * h + 0], l4);
-                        r.y = logp_cell_finish(l1, acc[i][4 * h + 1], l4);
-                        r.z = logp_cell_finish(l1, acc[i][4 * h + 2], l4);
-                        r.w = logp_cell_finish(l1, acc[i][4 * h + 3], l4);
+                        if (mean_only) {
+                            const float4 l2 = *reinterpret_cast<const float4 *>(sL2 + 32 * h + 4 * cg);
+                            r.x = logp_cell_finish_mean_only(l1, l2.x, acc[i][4 * h + 0], l4);
+                            r.y = logp_cell_finish_mean_only(l1, l2.y, acc[i][4 * h + 1], l4);
+                            r.z = logp_cell_finish_mean_only(l1, l2.z, acc[i][4 * h + 2], l4);
+                            r.w = logp_cell_finish_mean_only(l1, l2.w, acc[i][4 * h + 3], l4);
+                        } else {
+                            r.x = logp_cell_finish(l1, acc[i][4 * h + 0], l4);
+                            r.y = logp_cell_finish(l1, acc[i][4 * h + 1], l4);
+                            r.z = logp_cell_finish(l1, acc[i][4 * h + 2], l4);
+                            r.w = logp_cell_finish(l1, acc[i][4 * h + 3], l4);
+                        }
                         *reinterpret_cast<float4 *>(row + y) = r;
                     }
                 }

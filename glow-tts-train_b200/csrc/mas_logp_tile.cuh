@@ -67,6 +67,10 @@ __device__ __forceinline__ void logp_cell_fma(float &c, float inv_var, float mea
 
 // Final adds (models.py:376).
 __device__ __forceinline__ float logp_cell_finish(float l1, float c, float l4) { return (l1 + c) + l4; }
+// mean_only: l2 is the per-frame sum of -0.5 z^2 and the reference's own order applies, ((l1+l2)+l3)+l4
+__device__ __forceinline__ float logp_cell_finish_mean_only(float l1, float l2, float l3, float l4) {
+    return ((l1 + l2) + l3) + l4;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Register-tiled contraction: every thread owns a TM (tokens) x 8 (frames) block of cells.
@@ -84,7 +88,9 @@ constexpr int kGemmFrames = 64;   // frames per chunk
 constexpr int kGemmTM = 4;        // tokens per thread
 
 // kD: compile-time channel count (80 mel channels, the case that matters) or 0 = run-time D
-template <int TM, bool kInit, int kD>
+// kMeanOnly: logs == 0 (config.py:52 `mean_only`, the reference default): inv_var == 1, so the
+// inv_var term is a per-FRAME sum handled by the caller and only the mean term is contracted here.
+template <int TM, bool kInit, int kD, bool kMeanOnly>
 __device__ __forceinline__ void gemm_tile_d(const float *__restrict__ sInv, const float *__restrict__ sMiv,
                                             const float *__restrict__ sZ, int D_rt, int tile_rows, int rg, int cg,
                                             float (&acc)[TM][8]) {
@@ -103,24 +109,29 @@ __device__ __forceinline__ void gemm_tile_d(const float *__restrict__ sInv, cons
         float av[TM], bv[TM];
 #pragma unroll
         for (int q = 0; q < TM / 4; ++q) {
-            const float4 a = *reinterpret_cast<const float4 *>(pa + 4 * q), b = *reinterpret_cast<const float4 *>(pb + 4 * q);
-            av[4 * q] = a.x, av[4 * q + 1] = a.y, av[4 * q + 2] = a.z, av[4 * q + 3] = a.w;
+            const float4 b = *reinterpret_cast<const float4 *>(pb + 4 * q);
             bv[4 * q] = b.x, bv[4 * q + 1] = b.y, bv[4 * q + 2] = b.z, bv[4 * q + 3] = b.w;
+            if (!kMeanOnly) {
+                const float4 a = *reinterpret_cast<const float4 *>(pa + 4 * q);
+                av[4 * q] = a.x, av[4 * q + 1] = a.y, av[4 * q + 2] = a.z, av[4 * q + 3] = a.w;
+            }
         }
         const float4 z0 = *reinterpret_cast<const float4 *>(pz), z1 = *reinterpret_cast<const float4 *>(pz + 32);
         pa += tile_rows;
         pb += tile_rows;
         pz += kGemmFrames;
         const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-        float qv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) qv[j] = -0.5f * (zv[j] * zv[j]);      // models.py:368
         // Same per-cell order as logp_cell_fma (first the inv_var term, then the mean term), issued
         // as two sweeps over the register tile so that consecutive FFMAs share an operand.
+        if (!kMeanOnly) {
+            float qv[8];
 #pragma unroll
-        for (int i = 0; i < TM; ++i)
+            for (int j = 0; j < 8; ++j) qv[j] = -0.5f * (zv[j] * zv[j]);      // models.py:368
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], qv[j], acc[i][j]);
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], qv[j], acc[i][j]);
+        }
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -128,14 +139,14 @@ __device__ __forceinline__ void gemm_tile_d(const float *__restrict__ sInv, cons
     }
 }
 
-template <int TM, bool kInit>
+template <int TM, bool kInit, bool kMeanOnly = false>
 __device__ __forceinline__ void gemm_tile(const float *__restrict__ sInv, const float *__restrict__ sMiv,
                                           const float *__restrict__ sZ, int D, int tile_rows, int rg, int cg,
                                           float (&acc)[TM][8]) {
     if (D == 80)
-        gemm_tile_d<TM, kInit, 80>(sInv, sMiv, sZ, D, tile_rows, rg, cg, acc);
+        gemm_tile_d<TM, kInit, 80, kMeanOnly>(sInv, sMiv, sZ, D, tile_rows, rg, cg, acc);
     else
-        gemm_tile_d<TM, kInit, 0>(sInv, sMiv, sZ, D, tile_rows, rg, cg, acc);
+        gemm_tile_d<TM, kInit, 0, kMeanOnly>(sInv, sMiv, sZ, D, tile_rows, rg, cg, acc);
 }
 
 }  // namespace mas
