@@ -15,7 +15,9 @@ entry point raises.
 """
 from . import _lib, alignment, monotonic_align  # noqa: F401
 from .alignment import (  # noqa: F401
+    expand_prior,
     fused_maximum_path,
+    log_durations,
     log_likelihood_matrix,
     maximum_path_from_lengths,
 )
@@ -26,6 +28,8 @@ __all__ = [
     "maximum_path_from_lengths",
     "fused_maximum_path",
     "log_likelihood_matrix",
+    "expand_prior",
+    "log_durations",
     "monotonic_align",
     "alignment",
 ]

@@ -29,6 +29,9 @@ EXPORTED_SYMBOLS = (
     "mas_b200_logp_f32",
     "mas_b200_fused_maximum_path_f32",
     "mas_b200_maximum_path_host_i32",
+    "mas_b200_expand_prior_f32",
+    "mas_b200_expand_prior_backward_f32",
+    "mas_b200_log_durations_f32",
 )
 
 _lib = None
@@ -79,6 +82,12 @@ def load() -> ctypes.CDLL:
         _vp, _sz,
         _i32, _i32, _i32, _i32, _f32, _vp,
     ]
+    lib.mas_b200_expand_prior_f32.restype = _i32
+    lib.mas_b200_expand_prior_f32.argtypes = [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]
+    lib.mas_b200_expand_prior_backward_f32.restype = _i32
+    lib.mas_b200_expand_prior_backward_f32.argtypes = [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]
+    lib.mas_b200_log_durations_f32.restype = _i32
+    lib.mas_b200_log_durations_f32.argtypes = [_vp, _vp, _vp, _i32, _i32, _vp]
     lib.mas_b200_maximum_path_host_i32.restype = _i32
     lib.mas_b200_maximum_path_host_i32.argtypes = [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32]
     _lib = lib

@@ -138,3 +138,66 @@ def fused_maximum_path(x_m, x_logs, z, x_lengths, y_lengths, *, want_durations=T
             B, D, T_x, T_y, max_neg_val, _stream(dev))
     _lib.check(rc, "mas_b200_fused_maximum_path_f32")
     return _pack(path, durations, frame_token)
+
+
+# ------------------------------------------------------------------------------------------------
+# the path's consumers: models.py:383-393 without the dense path
+# ------------------------------------------------------------------------------------------------
+class _ExpandPrior(torch.autograd.Function):
+    """z[b,d,y] = x[b,d,frame_token[b,y]] -- what ``(attn^T @ x^T)^T`` computes (models.py:383-392),
+    as a gather; the backward is the segmented sum over each token's run of frames."""
+
+    @staticmethod
+    def forward(ctx, x, frame_token, durations):
+        lib = _lib.load()
+        _require_cuda(x, "x")
+        if x.dtype != torch.float32 or x.dim() != 3:
+            raise TypeError("x must be a float32 [B, D, T_x] tensor")
+        x = x.contiguous()
+        B, D, T_x = x.shape
+        T_y = frame_token.shape[1]
+        z = torch.empty((B, D, T_y), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.mas_b200_expand_prior_f32(x.data_ptr(), frame_token.data_ptr(), z.data_ptr(), B, D, T_x, T_y,
+                                               _stream(x.device))
+        _lib.check(rc, "mas_b200_expand_prior_f32")
+        ctx.save_for_backward(durations)
+        ctx.shape = (B, D, T_x, T_y)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lib = _lib.load()
+        (durations,) = ctx.saved_tensors
+        B, D, T_x, T_y = ctx.shape
+        dz = dz.contiguous().float()
+        dx = torch.empty((B, D, T_x), dtype=torch.float32, device=dz.device)
+        with torch.cuda.device(dz.device):
+            rc = lib.mas_b200_expand_prior_backward_f32(dz.data_ptr(), durations.data_ptr(), dx.data_ptr(), B, D, T_x, T_y,
+                                                        _stream(dz.device))
+        _lib.check(rc, "mas_b200_expand_prior_backward_f32")
+        return dx, None, None
+
+
+def expand_prior(x, frame_token, durations):
+    """Frame-level prior from the token-level one: ``z_m = expand_prior(x_m, frame_token, durations)``
+    replaces ``torch.matmul(attn.squeeze(1).transpose(1, 2), x_m.transpose(1, 2)).transpose(1, 2)``
+    (models.py:383-387; same for ``x_logs``, :388-392).  Differentiable w.r.t. ``x``."""
+    if frame_token.dtype != torch.int32 or durations.dtype != torch.int32:
+        raise TypeError("frame_token and durations must be int32 (as fused_maximum_path returns them)")
+    return _ExpandPrior.apply(x, frame_token.contiguous(), durations.contiguous())
+
+
+def log_durations(durations, x_lengths):
+    """``logw_ = torch.log(1e-8 + torch.sum(attn, -1)) * x_mask`` (models.py:393) from the integer
+    durations: fp32 [B, 1, T_x]."""
+    lib = _lib.load()
+    _require_cuda(durations, "durations")
+    B, T_x = durations.shape
+    x_len = x_lengths.to(device=durations.device, dtype=torch.int32).contiguous()
+    out = torch.empty((B, 1, T_x), dtype=torch.float32, device=durations.device)
+    with torch.cuda.device(durations.device):
+        rc = lib.mas_b200_log_durations_f32(durations.contiguous().data_ptr(), x_len.data_ptr(), out.data_ptr(), B, T_x,
+                                            _stream(durations.device))
+    _lib.check(rc, "mas_b200_log_durations_f32")
+    return out

@@ -162,6 +162,31 @@ int mas_b200_fused_maximum_path_f32(const float *x_m, const float *x_logs, const
                                      workspace_bytes - w.logp_bytes, B, T_x, T_y, max_neg_val, stream);
 }
 
+int mas_b200_expand_prior_f32(const float *x, const int32_t *frame_token, float *z, int B, int D, int T_x, int T_y,
+                              mas_stream_t stream) {
+    if (B < 0 || D < 0 || T_x < 0 || T_y < 0) return MAS_ERR_INVALID_ARGUMENT;
+    if (!shape_ok(B, T_x, T_y)) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (B == 0 || D == 0 || T_y == 0) return MAS_OK;
+    if (!x || !frame_token || !z) return MAS_ERR_INVALID_ARGUMENT;
+    return launch_expand_gather(x, frame_token, z, B, D, T_x, T_y, static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_expand_prior_backward_f32(const float *dz, const int32_t *durations, float *dx, int B, int D, int T_x, int T_y,
+                                       mas_stream_t stream) {
+    if (B < 0 || D < 0 || T_x < 0 || T_y < 0) return MAS_ERR_INVALID_ARGUMENT;
+    if (!shape_ok(B, T_x, T_y)) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (B == 0 || D == 0 || T_x == 0) return MAS_OK;
+    if (!dz || !durations || !dx) return MAS_ERR_INVALID_ARGUMENT;
+    return launch_expand_scatter(dz, durations, dx, B, D, T_x, T_y, static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_log_durations_f32(const int32_t *durations, const int32_t *x_len, float *logw, int B, int T_x, mas_stream_t stream) {
+    if (B < 0 || T_x < 0) return MAS_ERR_INVALID_ARGUMENT;
+    if (B == 0 || T_x == 0) return MAS_OK;
+    if (!durations || !x_len || !logw) return MAS_ERR_INVALID_ARGUMENT;
+    return launch_logw(durations, x_len, logw, B, T_x, static_cast<cudaStream_t>(stream));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-buffer entry: staging buffers are cached per device and grown on demand.
 // ---------------------------------------------------------------------------------------------

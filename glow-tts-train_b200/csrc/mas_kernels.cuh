@@ -37,6 +37,11 @@ size_t path_systolic_workspace_bytes(int B, int T_x, int T_y);
 int launch_path_systolic(PathParams p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 void path_systolic_force_cluster(int k);   // testing hook: CTAs per utterance (0 = heuristic)
 
+// path consumers (mas_expand.cu)
+int launch_expand_gather(const float *x, const int32_t *frame_token, float *z, int B, int D, int T_x, int T_y, cudaStream_t stream);
+int launch_expand_scatter(const float *dz, const int32_t *durations, float *dx, int B, int D, int T_x, int T_y, cudaStream_t stream);
+int launch_logw(const int32_t *durations, const int32_t *x_len, float *logw, int B, int T_x, cudaStream_t stream);
+
 // developer profiling hook: when non-null, kernels stamp clock64() phase times into it
 extern long long *g_dbg_cycles;
 

@@ -135,6 +135,20 @@ int mas_b200_fused_maximum_path_f32(const float *x_m, const float *x_logs, const
                                     mas_stream_t stream);
 
 /*
+ * The path's consumers (models.py:383-393) without the dense path:
+ *   expand_prior           z[b,d,y] = x[b,d,frame_token[b,y]] (0 where frame_token < 0): what
+ *                          (attn^T @ x^T)^T computes for x = x_m / x_logs (models.py:383-392), exactly
+ *   expand_prior_backward  dx[b,d,x] = sum of dz[b,d,y] over token x's run of frames (durations)
+ *   log_durations          logw_[b,x] = log(1e-8 + durations[b,x]) for x < x_len[b], else 0 (models.py:393)
+ * x, z: [B][D][T_x] / [B][D][T_y] fp32 contiguous; frame_token int32 [B][T_y]; durations int32 [B][T_x].
+ */
+int mas_b200_expand_prior_f32(const float *x, const int32_t *frame_token, float *z, int B, int D, int T_x, int T_y,
+                              mas_stream_t stream);
+int mas_b200_expand_prior_backward_f32(const float *dz, const int32_t *durations, float *dx, int B, int D, int T_x, int T_y,
+                                       mas_stream_t stream);
+int mas_b200_log_durations_f32(const int32_t *durations, const int32_t *x_len, float *logw, int B, int T_x, mas_stream_t stream);
+
+/*
  * Host-buffer convenience used for end-to-end timing and by non-torch callers: takes HOST
  * pointers with the layout of maximum_path_c (core.pyx:40) -- values fp32 [B][T_x][T_y]
  * C-contiguous (NOT clobbered), t_xs / t_ys int32 [B], paths int32 [B][T_x][T_y] (fully written)

@@ -33,7 +33,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor", "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max"]
 traffic = {}
-for tag in ("mas", "logp"):
+for tag in ("mas", "fused"):
     rep = src / f"{R}_prof_{tag}.ncu-rep"
     if not rep.exists():
         continue
@@ -57,7 +57,7 @@ for tag in ("mas", "logp"):
         x = float(c.replace(",", ""))
         return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
     traffic[tag] = mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
-json.dump({"c2": traffic.get("mas"), "c1": traffic.get("mas"), "logp_c2": traffic.get("logp"),
+json.dump({"c2": traffic.get("fused"), "c1": traffic.get("mas"), "fused_c2": traffic.get("fused"),
            "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, B=32 200x1000"},
           open(out / "traffic.json", "w"), indent=1)
 print(open(out / f"{R}_launches.txt").read())
