@@ -52,7 +52,7 @@ __host__ __device__ inline Plan make_plan(int R, int W, int S, int K, int T_y, b
     p.off_bnd = off;
     off += (W + 1) * kBndBlocks * kBlk * 4;       // ring w = boundary INTO warp w; ring 0 is constant -1e9
     p.off_bar = off;
-    off += W * S * 8;
+    off += 2 * W * S * 8;                         // full[W][S] then empty[W][S]
     p.off_done = off;
     off += (W + 2) * 4;                           // [prev CTA's last warp | own warps | next CTA's first warp]
     p.off_misc = off;
@@ -227,27 +227,41 @@ static __device__ __noinline__ void exact_sweep_cta0(const float *__restrict__ v
 template <bool kSmem>
 __device__ __forceinline__ int backtrack_tokens(const uint32_t *bits, int rows, int xc, int x, int y_hi, int x_min,
                                                 int2 *run) {
+    // One step per (token, block) word the path touches: either the path stepped onto x inside this
+    // block (-> next token, same block) or it did not (-> same token, previous block).  A lone thread
+    // issues an instruction every ~2.3 cycles and pays ~25 per branch, so: both successor words are
+    // fetched before the decision, the decision is a handful of selects, four steps per loop trip.
+    // In shared memory the successor loads are unconditional (a word before / a row above the table
+    // is still this CTA's shared memory -- the plan puts the sweep ring there -- and is never used).
     int base = y_hi & ~31;
     uint32_t elig = 0xffffffffu >> (31 - (y_hi & 31));     // bits at or below the scan position
     const uint32_t *p = bits + (size_t)(y_hi >> 5) * rows + (x - xc);
-    int2 *r = run + (x - xc);
-    // Branches are what a lone thread pays for (~25 cycles each): one per token, two per block.
-    while (x >= x_min) {
-        uint32_t m = (kSmem ? *p : __ldcg(p)) & elig;
-        while (m != 0u) {                                   // the path stepped onto x inside this block
-            const uint32_t wn = (x > x_min) ? (kSmem ? p[-1] : __ldcg(p - 1)) : 0u;   // next token, same block
+    run -= xc;                                              // indexed by the global token number
+    uint32_t w = kSmem ? *p : __ldcg(p);
+    while (x >= x_min && base >= 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint32_t w_left, w_up;
+            if (kSmem) {
+                w_left = p[-1];                             // next token, same block
+                w_up = *(p - rows);                         // same token, previous block
+            } else {
+                w_left = (x > x_min) ? __ldcg(p - 1) : 0u;
+                w_up = (base > 0) ? __ldcg(p - rows) : 0u;
+            }
+            const bool alive = x >= x_min && base >= 0;
+            const uint32_t m = alive ? (w & elig) : 0u;
+            const bool step = m != 0u;                      // the path stepped onto x inside this block
             const int lo = 31 - __clz(m);
-            *r = make_int2(base + lo, y_hi);
-            y_hi = base + lo - 1;
-            --x;
-            --p;
-            --r;
-            elig = (1u << lo) - 1u;                         // lo == 0: nothing left here, leave the block
-            m = wn & elig;                                  // x < x_min: wn == 0 ends both loops
+            const int y_lo = base + lo;
+            if (step) run[x] = make_int2(y_lo, y_hi);
+            y_hi = step ? y_lo - 1 : y_hi;
+            p = step ? p - 1 : p - rows;                    // (dead steps wander; nothing is dereferenced for use)
+            elig = step ? (1u << lo) - 1u : 0xffffffffu;    // lo == 0: nothing left here, the next step goes up
+            base -= (step || !alive) ? 0 : 32;
+            x -= step ? 1 : 0;
+            w = step ? w_left : w_up;
         }
-        base -= 32;                                         // same token, previous block
-        p -= rows;
-        elig = 0xffffffffu;
     }
     return y_hi;
 }
@@ -275,7 +289,8 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
     uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem + plan.off_bits);
     uint32_t *bits_g = bits_smem ? nullptr : p.ws_bits + ((size_t)b * K + c) * plan.nblk * rows;
     float *bnd = reinterpret_cast<float *>(smem + plan.off_bnd);       // [W+1][kBndBlocks*32]; ring w = INTO warp w
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + plan.off_bar);   // [W][S]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + plan.off_bar);   // [W][S] box landed (TMA complete_tx)
+    uint64_t *empty = full + W * S;                                        // [W][S] box consumed (lane 0 of the sweep warp)
     // progress counters: [0] = last warp of the previous CTA (written over DSMEM), [1+w] = own warp w,
     // [W+1] = first warp of the next CTA (written over DSMEM)
     int *done = reinterpret_cast<int *>(smem + plan.off_done);
@@ -323,7 +338,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         cbend = min(ty - 1, x1 + (ty - tx)) >> 5;            // ... and token x1 leaves it here (core.pyx:18)
     }
     if (tid == 0) {
-        for (int i = 0; i < W * S; ++i) ptx::mbar_init(&full[i], 1);
+        for (int i = 0; i < 2 * W * S; ++i) ptx::mbar_init(&full[i], 1);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
         done[0] = (c == 0) ? kDoneAll : -1;                  // CTA 0 has no predecessor (its ring 0 is constant)
@@ -357,15 +372,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         if (active) {
             float *my_ring = ring + (size_t)warp * S * (rows_per_warp * kBlk);
             uint64_t *my_full = full + warp * S;
-            constexpr uint32_t box_bytes = kBlk * R * kBlk * 4;
-            if (lane == 0) {
-                ptx::prefetch_tensormap(&tmap);
-                for (int k = 0; k < S && cb0 + k <= cbend; ++k) {
-                    if (kFused) wait_chunk_ready(ready, (cb0 + k) >> 1, ready_target);
-                    ptx::mbar_arrive_expect_tx(&my_full[k], box_bytes);
-                    ptx::tma_load_3d(my_ring + (size_t)k * rows_per_warp * kBlk, &tmap, &my_full[k], (cb0 + k) * kBlk, x0, b);
-                }
-            }
+            uint64_t *my_empty = empty + warp * S;
             float v[R];
             uint32_t acc[R];
 #pragma unroll
@@ -453,9 +460,8 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                     ptx::st_release_cluster_if(lane31 && mirror_next != 0u, mirror_next, cb + 1);
                 }
                 ptx::st_release_shared_if(lane31, &done[1 + warp], cb + 1);
-                __syncwarp();                                  // every lane has read the box: refill the slot
-                if (kFused && lane0 && cb + S <= cbend) wait_chunk_ready(ready, (cb + S) >> 1, ready_target);
-                ptx::tma_load_3d_if(lane0 && cb + S <= cbend, tile, &tmap, &my_full[slot], box_bytes, (cb + S) * kBlk, x0, b);
+                __syncwarp();                                  // every lane has read the box: hand the slot back
+                ptx::mbar_arrive_if(lane0, &my_empty[slot]);   // the loader warp refills it
                 if (++slot == S) {
                     slot = 0;
                     parity ^= 1u;
@@ -484,24 +490,65 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
             dbg[10] = cbend - cb0 + 1;
         }
     } else if (filler_warp) {
-        // ---- filler warp: zero this CTA's slice of the dense output while the sweep runs ----
-        // One lane streams a shared zero page to global memory with bulk async copies (UBLKCP):
-        // a few dozen instructions for the whole slab instead of a flood of vector stores that
-        // would compete with the sweep warps for the load/store pipe.
+        // ---- loader / filler warp ----
+        // (1) zero this CTA's slice of the dense output with bulk async copies of a shared zero page
+        //     (UBLKCP: a few dozen instructions for the whole slab instead of a flood of vector
+        //     stores that would compete with the sweep warps for the load/store pipe);
+        // (2) feed every sweep warp's ring: wait for a slot to be handed back (`empty`), in the fused
+        //     launch also for the producers' ready flag of the chunk, arm `full`, issue the TMA box.
         float4 *zero4 = reinterpret_cast<float4 *>(smem + plan.off_zero);
         for (int i = lane; i < plan.zero_bytes / 16; i += 32) zero4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         ptx::fence_proxy_async();                              // generic writes -> visible to the async proxy
         __syncwarp();
-        const int my_rows = max(0, min(rows, T_x - xc));
-        if (lane == 0 && my_rows > 0) {
-            char *dst = reinterpret_cast<char *>(p.path + ((int64_t)b * T_x + xc) * T_y);
-            const int64_t total = (int64_t)my_rows * T_y * 4;    // multiple of 16: T_y % 4 == 0 on this path
-            for (int64_t off = 0; off < total; off += plan.zero_bytes) {
-                const int64_t n = total - off;
-                ptx::bulk_store_s2g(dst + off, zero4, (uint32_t)(n < plan.zero_bytes ? n : plan.zero_bytes));
+        {
+            // lane w feeds sweep warp w (state in registers, the W lanes poll in parallel); lane 0
+            // also drips one zero-fill bulk copy per pass
+            constexpr uint32_t box_bytes = kBlk * R * kBlk * 4;
+            if (lane == 0) ptx::prefetch_tensormap(&tmap);
+            const int wx0 = xc + lane * rows_per_warp;
+            const bool feeds = lane < W && wx0 < tx;
+            const int w_cb0 = feeds ? wx0 >> 5 : 0;
+            const int w_cbend = feeds ? min(ty - 1, min(wx0 + rows_per_warp, tx) - 1 + (ty - tx)) >> 5 : -1;
+            int k = 0;                                          // boxes issued so far
+            const int my_rows = max(0, min(rows, T_x - xc));
+            char *zdst = reinterpret_cast<char *>(p.path + ((int64_t)b * T_x + xc) * T_y);
+            const int64_t ztotal = (int64_t)my_rows * T_y * 4;  // multiple of 16: T_y % 4 == 0 on this path
+            int64_t zoff = lane == 0 ? 0 : ztotal;
+            uint32_t spins = 0;
+            for (;;) {
+                const bool want = w_cb0 + k <= w_cbend;
+                if (!__any_sync(0xffffffffu, want || zoff < ztotal)) break;
+                bool go = false;
+                if (want) {
+                    const int sl = k % S;
+                    // a slot's n-th reuse waits for its n-th hand-back; the first S boxes need none
+                    go = k < S || ptx::mbar_test_wait(&empty[lane * S + sl], (uint32_t)(((k / S) & 1) ^ 1));
+                    if (kFused && go) {
+                        go = ptx::ld_acquire_gpu(ready + ((w_cb0 + k) >> 1)) >= ready_target;
+                        if (go) ptx::fence_proxy_async_all();
+                    }
+                    if (go) {
+                        float *dst = ring + ((size_t)lane * S + sl) * (rows_per_warp * kBlk);
+                        ptx::mbar_arrive_expect_tx(&full[lane * S + sl], box_bytes);
+                        ptx::tma_load_3d(dst, &tmap, &full[lane * S + sl], (w_cb0 + k) * kBlk, wx0, b);
+                        ++k;
+                    }
+                }
+                if (zoff < ztotal) {
+                    const int64_t n = ztotal - zoff;
+                    ptx::bulk_store_s2g(zdst + zoff, zero4, (uint32_t)(n < plan.zero_bytes ? n : plan.zero_bytes));
+                    zoff += plan.zero_bytes;
+                    go = true;
+                }
+                if (!__any_sync(0xffffffffu, go)) {
+                    __nanosleep(32);
+                    if (++spins > kSpinLimit) spin_fail();
+                } 
             }
-            ptx::bulk_commit_group();
-            ptx::bulk_wait_all();                              // the ones are written after the next barrier
+            if (lane == 0 && ztotal > 0) {
+                ptx::bulk_commit_group();
+                ptx::bulk_wait_all();                          // the ones are written after the next barrier
+            }
         }
         __syncwarp();
         if (kDbg && dbg && lane == 0) dbg[1] = clock64();

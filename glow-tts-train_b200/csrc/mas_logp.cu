@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(224, 2) mas_logp_kernel(LogpParams p, Geometry
                     const float m = __ldg(xm + (int64_t)(d0 + d) * T_x + xg);
                     const float ls = xl ? __ldg(xl + (int64_t)(d0 + d) * T_x + xg) : 0.f;
                     const float r = xl ? expf(-2.0f * ls) : 1.0f;         // models.py:363
-                    sInv[d * tile_rows + x] = r;
+                    sInv[d * tile_rows + x] = -0.5f * r;                    // models.py:368
                     sMiv[d * tile_rows + x] = m * r;                        // models.py:371
                     l1 += kNegHalfLog2Pi - ls;                              // models.py:364-366
                     l4 = fmaf(-0.5f * (m * m), r, l4);                      // models.py:373-375

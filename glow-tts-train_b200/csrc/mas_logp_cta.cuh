@@ -69,28 +69,44 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
     }
     if (dbg_ns && tid == 0) dbg_ns[0] = ptx::globaltimer_ns();
     stage_frames_async(ch, 0);                          // in flight while the token side is prepared
-    // token side: thread x stages token x0+x for every channel (coalesced over x, eight loads in
-    // flight) and sums its row constants on the way, channels ascending
-    for (int x = tid; x < tile_rows; x += nthr) {
-        const int xg = x0 + x;
+    // token side: thread (x, h) stages token x0+x for one contiguous share of the channels (coalesced
+    // over x, eight loads in flight) and sums its share of the row constants, channels ascending;
+    // the shares are then added in order.  nsh = how many threads serve a token (2 at 224 / 112).
+    const int nsh = max(1, min(4, nthr / tile_rows));
+    const int dsh = ceil_div(D, nsh);
+    float *sPart = sZ + D * kGemmFrames;                // buffer 1 of sZ is still free: [nsh][2][tile_rows]
+    if (tid < nsh * tile_rows) {
+        const int h = tid / tile_rows, x = tid - h * tile_rows, xg = x0 + x;
+        const int d0 = h * dsh, d1 = min(D, d0 + dsh);
         float l1 = 0.f, l4 = 0.f;
         if (xg < T_x) {
 #pragma unroll 8
-            for (int d = 0; d < D; ++d) {
+            for (int d = d0; d < d1; ++d) {
                 const float m = __ldg(xm + (int64_t)d * T_x + xg);
                 const float ls = xl ? __ldg(xl + (int64_t)d * T_x + xg) : 0.f;
                 const float r = xl ? expf(-2.0f * ls) : 1.0f;         // models.py:363
-                sInv[d * tile_rows + x] = r;
+                sInv[d * tile_rows + x] = -0.5f * r;                    // models.py:368
                 sMiv[d * tile_rows + x] = m * r;                        // models.py:371
                 l1 += kNegHalfLog2Pi - ls;                              // models.py:364-366
                 l4 = fmaf(-0.5f * (m * m), r, l4);                      // models.py:373-375
             }
         } else {
-            for (int d = 0; d < D; ++d) sInv[d * tile_rows + x] = sMiv[d * tile_rows + x] = 0.f;
+            for (int d = d0; d < d1; ++d) sInv[d * tile_rows + x] = sMiv[d * tile_rows + x] = 0.f;
         }
-        sL1[x] = l1;
-        sL4[x] = l4;
+        sPart[(2 * h) * tile_rows + x] = l1;
+        sPart[(2 * h + 1) * tile_rows + x] = l4;
     }
+    __syncthreads();
+    if (tid < tile_rows) {
+        float l1 = sPart[tid], l4 = sPart[tile_rows + tid];
+        for (int h = 1; h < nsh; ++h) {
+            l1 += sPart[(2 * h) * tile_rows + tid];
+            l4 += sPart[(2 * h + 1) * tile_rows + tid];
+        }
+        sL1[tid] = l1;
+        sL4[tid] = l4;
+    }
+    __syncthreads();                                    // sPart is read before chunk 1 lands in that buffer
     float acc[kGemmTM][8];
     for (int k = 0; k < chunk_count; ++k) {
         const int buf = k & 1;

@@ -4,7 +4,9 @@
 //
 //   logp[x,y] = (l1[x] + c[x,y]) + l4[x]
 //   c[x,y]    = sum over channels d, ascending, ONE accumulator:
-//                   c = fma(inv_var[d,x], -0.5 z[d,y]^2, c)        (models.py:367-369, "logp2")
+//                   c = fma(-0.5 inv_var[d,x], z[d,y]^2, c)        (models.py:367-369, "logp2"; the
+//                       -0.5 rides on the token-side operand: a power of two, so the product is
+//                       the one the reference forms, and the inner loop has one FMUL per z less)
 //                   c = fma(m[d,x] inv_var[d,x], z[d,y], c)        (models.py:370-372, "logp3")
 //   l1[x]     = sum_d (-0.5 log(2 pi) - logs[d,x])                 (models.py:364-366)
 //   l4[x]     = sum_d -0.5 m[d,x]^2 inv_var[d,x]                   (models.py:373-375)
@@ -22,49 +24,6 @@ namespace mas {
 // that torch turns into the fp32 scalar of the tensor expression).
 constexpr float kNegHalfLog2Pi = -0.91893853320467274178f;
 
-// Token-side operands of channel d for token x: inv_var = exp(-2 logs) (models.py:363) and
-// m * inv_var (models.py:371).  Out-of-range tokens give zeros.
-__device__ __forceinline__ void token_operands(const float *__restrict__ xm, const float *__restrict__ xl,
-                                               int T_x, int d, int x, float &inv_var, float &mean_inv_var) {
-    if (x < T_x) {
-        const float m = __ldg(xm + (int64_t)d * T_x + x);
-        const float r = xl ? expf(-2.0f * __ldg(xl + (int64_t)d * T_x + x)) : 1.0f;
-        inv_var = r;
-        mean_inv_var = m * r;
-    } else {
-        inv_var = 0.f;
-        mean_inv_var = 0.f;
-    }
-}
-
-// Frame-side operands: z and -0.5 z^2 (models.py:368).
-__device__ __forceinline__ void frame_operands(const float *__restrict__ z, int T_y, int d, int y,
-                                               float &zv, float &neg_half_zsq) {
-    zv = (y < T_y) ? __ldg(z + (int64_t)d * T_y + y) : 0.f;
-    neg_half_zsq = -0.5f * (zv * zv);
-}
-
-// l1 and l4 of token x (models.py:364-366, 373-375), channels summed in ascending order.
-__device__ __forceinline__ void row_constants(const float *__restrict__ xm, const float *__restrict__ xl,
-                                              int D, int T_x, int x, float &l1, float &l4) {
-    l1 = 0.f;
-    l4 = 0.f;
-    if (x >= T_x) return;
-    for (int d = 0; d < D; ++d) {
-        const float m = __ldg(xm + (int64_t)d * T_x + x);
-        const float ls = xl ? __ldg(xl + (int64_t)d * T_x + x) : 0.f;
-        const float r = xl ? expf(-2.0f * ls) : 1.0f;
-        l1 += kNegHalfLog2Pi - ls;
-        l4 = fmaf(-0.5f * (m * m), r, l4);
-    }
-}
-
-// One channel of one cell.
-__device__ __forceinline__ void logp_cell_fma(float &c, float inv_var, float mean_inv_var, float neg_half_zsq, float zv) {
-    c = fmaf(inv_var, neg_half_zsq, c);
-    c = fmaf(mean_inv_var, zv, c);
-}
-
 // Final adds (models.py:376).
 __device__ __forceinline__ float logp_cell_finish(float l1, float c, float l4) { return (l1 + c) + l4; }
 // mean_only: l2 is the per-frame sum of -0.5 z^2 and the reference's own order applies, ((l1+l2)+l3)+l4
@@ -75,8 +34,8 @@ __device__ __forceinline__ float logp_cell_finish_mean_only(float l1, float l2, 
 // ---------------------------------------------------------------------------------------------
 // Register-tiled contraction: every thread owns a TM (tokens) x 8 (frames) block of cells.
 // Shared-memory operands:
-//   sInv, sMiv : [D][tile_rows]   token-side, token index contiguous
-//   sZ         : [D][64]          frame-side, a 64-frame chunk of z; -0.5 z^2 is formed in registers
+//   sInv, sMiv : [D][tile_rows]   token-side (-0.5 inv_var, m inv_var), token index contiguous
+//   sZ         : [D][64]          frame-side, a 64-frame chunk of z; z^2 is formed in registers
 // Thread (rg, cg): tokens TM rg .. TM rg + TM-1; frames {4 cg .. 4 cg + 3} and {32 + 4 cg .. 32 + 4 cg + 3},
 // so that the 8 column groups of a warp read one contiguous 128-byte line per LDS.128.
 // Measured on B200 (profiles/probes/probe_ffma2.cu, FFMA per cycle per SM of 128):
@@ -126,7 +85,7 @@ __device__ __forceinline__ void gemm_tile_d(const float *__restrict__ sInv, cons
         if (!kMeanOnly) {
             float qv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) qv[j] = -0.5f * (zv[j] * zv[j]);      // models.py:368
+            for (int j = 0; j < 8; ++j) qv[j] = zv[j] * zv[j];                // models.py:368, -0.5 is in av
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
