@@ -93,14 +93,19 @@ def _check_prior(x_m, x_logs, z):
     return B, D, T_x, z.shape[2]
 
 
-def log_likelihood_matrix(x_m, x_logs, z):
+def log_likelihood_matrix(x_m, x_logs, z, out=None):
     """models.py:362-376 on the GPU: ``x_m``/``x_logs`` [B,D,T_x] (``x_logs=None`` == zeros, the
-    mean_only configuration), ``z`` [B,D,T_y] -> logp fp32 [B,T_x,T_y]."""
+    mean_only configuration), ``z`` [B,D,T_y] -> logp fp32 [B,T_x,T_y] (written into ``out`` when
+    given: contiguous fp32 of that shape on the same device)."""
     lib = _lib.load()
     B, D, T_x, T_y = _check_prior(x_m, x_logs, z)
     x_m, z = x_m.contiguous(), z.contiguous()
     x_logs = x_logs.contiguous() if x_logs is not None else None
-    out = torch.empty((B, T_x, T_y), dtype=torch.float32, device=x_m.device)
+    if out is None:
+        out = torch.empty((B, T_x, T_y), dtype=torch.float32, device=x_m.device)
+    elif (out.dtype != torch.float32 or out.device != x_m.device or tuple(out.shape) != (B, T_x, T_y)
+          or not out.is_contiguous()):
+        raise ValueError("out must be a contiguous float32 [B, T_x, T_y] tensor on the inputs' device")
     if out.numel() == 0:
         return out
     with torch.cuda.device(x_m.device):

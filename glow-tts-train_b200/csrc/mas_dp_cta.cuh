@@ -63,17 +63,6 @@ __host__ __device__ inline Plan make_plan(int R, int W, int S, int K, int T_y, b
 
 __device__ __forceinline__ void spin_fail() { __trap(); }
 
-// Fused launch: block until the producer CTAs have stored 64-frame chunk `chunk` of this utterance's
-// scores (acquire at GPU scope), then order those generic-proxy writes before our TMA read.
-__device__ __forceinline__ void wait_chunk_ready(const int *ready, int chunk, int target) {
-    uint32_t spins = 0;
-    while (ptx::ld_acquire_gpu(ready + chunk) < target) {
-        __nanosleep(256);                               // the producers may share this SM: do not burn issue slots
-        if (++spins > kSpinLimit) spin_fail();
-    }
-    ptx::fence_proxy_async_all();
-}
-
 __device__ __forceinline__ float fmax_nan(float a, float b) {
     float r;
     asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
@@ -268,12 +257,14 @@ __device__ __forceinline__ int backtrack_tokens(const uint32_t *bits, int rows, 
 
 // The whole per-CTA program of kernel (1): lengths, sweep, (exact redo), backtrack, dense output.
 // kCluster: compiled with the distributed-shared-memory paths (K > 1); the K == 1 build carries none.
-// kFused: the scores are produced by other CTAs of the same launch (mas_fused.cu): every box load
-// first waits for the ready flag of the 64-frame chunk it reads (`ready[b][chunk] >= ready_target`).
+// kFused: the scores are produced by other CTAs of the same launch (mas_fused.cu) in chunks of
+// `chunk_frames` frames: every box load first waits for the ready flags of the chunks it reads
+// (`ready[chunk] >= ready_target`, acquire at GPU scope, then a proxy fence before the TMA read).
 // `b`: utterance; `cta_tag`: index for the profiling buffer; warps beyond plan.W + 1 idle.
 template <int R, bool kDbg, bool kCluster, bool kFused>
 __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams &p, const Plan &plan, unsigned char *smem,
-                                       int b, int cta_tag, const int *ready, int ready_target) {
+                                       int b, int cta_tag, const int *ready, int ready_target, int chunk_frames = 64,
+                                       int nchunks = 0) {
     float *s_len = reinterpret_cast<float *>(smem + plan.off_misc + 16);
 
     const int K = kCluster ? plan.K : 1;
@@ -409,7 +400,6 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                 const long long t0 = kDbg ? clock64() : 0;
                 while (seen_prev <= cb) {                       // previous warp has published block cb
                     seen_prev = prev_remote ? ptx::ld_acquire_cluster_shared(&done[warp]) : ptx::ld_acquire_shared(&done[warp]);
-                    if (kFused && seen_prev <= cb) __nanosleep(128);   // a producer CTA may share this SM
                     if (++spins > kSpinLimit) spin_fail();
                 }
                 while (seen_next + kBndBlocks <= cb) {          // next warp has consumed block cb - ring depth
@@ -524,7 +514,11 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                     // a slot's n-th reuse waits for its n-th hand-back; the first S boxes need none
                     go = k < S || ptx::mbar_test_wait(&empty[lane * S + sl], (uint32_t)(((k / S) & 1) ^ 1));
                     if (kFused && go) {
-                        go = ptx::ld_acquire_gpu(ready + ((w_cb0 + k) >> 1)) >= ready_target;
+                        // the box spans frames [f0, f0 + 32): one or two of the producers' chunks
+                        const int f0 = (w_cb0 + k) * kBlk;
+                        const int c0 = f0 / chunk_frames, c1 = min((f0 + kBlk - 1) / chunk_frames, nchunks - 1);
+                        go = ptx::ld_acquire_gpu(ready + c0) >= ready_target;
+                        if (go && c1 != c0) go = ptx::ld_acquire_gpu(ready + c1) >= ready_target;
                         if (go) ptx::fence_proxy_async_all();
                     }
                     if (go) {

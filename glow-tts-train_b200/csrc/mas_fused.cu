@@ -1,16 +1,20 @@
 // mas_fused.cu -- kernel (2): log-likelihood + alignment search in ONE launch (models.py:362-382).
 //
-// Two kinds of CTAs share the grid and run concurrently:
-//   * producers (blockIdx < n_gemm): the FFMA contraction of mas_logp_cta.cuh for one tile of tokens
-//     of one utterance, walking 64-frame chunks in an interleaved order (producer j of n takes
-//     chunks j, j+n, j+2n, ...) so that the scores of EARLY frames of every utterance exist first;
-//     after each chunk is stored they raise that chunk's ready flag (fence + red.release.gpu);
-//   * one sweep CTA per utterance: kernel (1)'s program (mas_dp_cta.cuh) whose TMA box loads wait
-//     for the flag of the chunk they read (ld.acquire.gpu + fence.proxy.async), so the systolic
+// One CTA per SM, two kinds sharing the grid and running concurrently:
+//   * producers (blockIdx < P): the FFMA contraction of mas_logp_cta.cuh, 16 warps, a token tile of
+//     one utterance resident in shared memory, walking chunks in an interleaved order (Deal:
+//     producer j of the d on a tile takes chunks j, j+d, ...) so that the scores of EARLY frames of
+//     every utterance exist first; after each chunk is stored they raise that chunk's ready flag
+//     (fence + red.release.gpu);
+//   * one sweep CTA per utterance: kernel (1)'s program (mas_dp_cta.cuh) whose loader warp waits for
+//     the flags of the chunks a TMA box reads (ld.acquire.gpu + fence.proxy.async), so the systolic
 //     sweep trails the producers by a few blocks instead of starting after the last FFMA.
+// A sweep warp runs alone on its scheduler at ~0.45 IPC; sharing the SM with FFMA warps halved its
+// speed and made it the tail of the launch (profiles/r1_fused_timeline.txt, first layout), so a sweep
+// CTA now has its SM to itself: the shared-memory request is sized so that only one CTA fits.
 // Producers never wait for anybody and carry the lower block indices, so the launch cannot
-// deadlock whatever the residency; with both programs under half an SM's shared memory two CTAs
-// share an SM and the whole grid is resident for the training shapes.
+// deadlock whatever the residency.  With more utterances than a third of the SMs the two kernels
+// run back to back instead (the caller's fallback).
 //
 // The scores travel through a [B,T_x,T_y] fp32 scratch in the caller's workspace, written once and
 // read once while still in the 126 MB L2 (25.6 MB for B=32, 200x1000).
@@ -26,32 +30,27 @@
 namespace mas {
 namespace fused {
 
-constexpr int kThreads = 224;          // producers: 28 token groups of 4 x 8 frame groups | sweep CTAs use 160 of them
+constexpr int kThreads = kGemmThreads;          // producers: 16 warps | sweep CTAs use W + 1 of them
 
 struct Geometry {
-    int n_gemm;        // producer CTAs = B * row_tiles * n_per
-    int row_tiles, tile_rows, n_per, nchunks;
+    int P;             // producer CTAs
+    TileShape t;
+    logp::Deal deal;
     int *ready;        // [B][nchunks] chunk ready counters
-    int *queue;        // [B][row_tiles] next chunk to contract, per token tile
 };
 
 template <int R, bool kDbg>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 mas_fused_kernel(const __grid_constant__ CUtensorMap tmap, PathParams pp, systolic::Plan plan, LogpParams lp, Geometry g) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    if ((int)blockIdx.x < g.n_gemm) {
-        // producer j of the n that share a token tile takes chunks j, j+n, j+2n, ...  (a shared chunk
-        // queue and dealing the producers out across SMs were tried: no better)
-        const int j = blockIdx.x % g.n_per, t = blockIdx.x / g.n_per;
-        const int rt = t % g.row_tiles, b = t / g.row_tiles;
-        const int count = (g.nchunks - j + g.n_per - 1) / g.n_per;
+    if ((int)blockIdx.x < g.P) {
         // profiling: producers stamp globaltimer per chunk behind the sweep CTAs' [B][16][16] block
         long long *dbg_ns = (kDbg && pp.dbg_cycles) ? pp.dbg_cycles + ((size_t)pp.B * 16 + blockIdx.x) * 16 : nullptr;
-        logp::logp_cta<true>(lp, reinterpret_cast<float *>(smem), g.tile_rows, b, rt * g.tile_rows, j, g.n_per, count,
-                             g.ready + (size_t)b * g.nchunks, dbg_ns);
+        logp::run_deal<true>(lp, reinterpret_cast<float *>(smem), g.t, g.deal, blockIdx.x, g.ready, dbg_ns);
     } else {
-        const int b = blockIdx.x - g.n_gemm;
-        systolic::dp_cta<R, kDbg, false, true>(tmap, pp, plan, smem, b, b, g.ready + (size_t)b * g.nchunks, g.row_tiles);
+        const int b = blockIdx.x - g.P;
+        systolic::dp_cta<R, kDbg, false, true>(tmap, pp, plan, smem, b, b, g.ready + (size_t)b * g.t.nchunks, g.t.row_tiles,
+                                               g.t.F, g.t.nchunks);
     }
 }
 
@@ -63,7 +62,7 @@ static int launch_r(const CUtensorMap &tmap, const PathParams &pp, const systoli
     MAS_CUDA_TRY(cudaGetDevice(&dev));
     if (pp.dbg_cycles != nullptr) {
         MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        mas_fused_kernel<R, true><<<g.n_gemm + pp.B, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
+        mas_fused_kernel<R, true><<<g.P + pp.B, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
         MAS_CUDA_TRY(cudaGetLastError());
         return MAS_OK;
     }
@@ -78,15 +77,15 @@ static int launch_r(const CUtensorMap &tmap, const PathParams &pp, const systoli
         cudaFuncGetAttributes(&fa, mas_fused_kernel<R, false>);
         fprintf(stderr, "[mas_b200] fused kernel: %d CTAs/SM resident, %d regs, %zu B static smem\n", nb, fa.numRegs, fa.sharedSizeBytes);
     }
-    mas_fused_kernel<R, false><<<g.n_gemm + pp.B, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
+    mas_fused_kernel<R, false><<<g.P + pp.B, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
     MAS_CUDA_TRY(cudaGetLastError());
     return MAS_OK;
 }
 
 }  // namespace fused
 
-static size_t fused_flag_bytes(int B, int T_y) {      // ready counters + per-tile chunk queues (<= 32 tiles per utterance)
-    return align_up((size_t)B * (ceil_div(T_y, kGemmFrames) + 32) * 4, 256);
+static size_t fused_flag_bytes(int B, int T_y) {      // ready counters, one per chunk (chunks are >= 64 frames)
+    return align_up((size_t)B * (ceil_div(T_y, 8 * kGemmMinCG) + 1) * 4, 256);
 }
 
 size_t fused_workspace_bytes(int B, int D, int T_x, int T_y) {
@@ -107,7 +106,7 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
         (reinterpret_cast<uintptr_t>(lp_in.z) & 15) || (reinterpret_cast<uintptr_t>(path) & 15))
         MAS_FUSED_NO("alignment / frame count / channel count");
     int R, W;
-    if (!systolic::choose_shape(T_x, R, W) || W > 4) MAS_FUSED_NO("more than 4 sweep warps");
+    if (!systolic::choose_shape(T_x, R, W) || (W + 1) * 32 > kThreads) MAS_FUSED_NO("too many sweep warps");
     PFN_cuTensorMapEncodeTiled_v12000 encode = systolic::get_encode_fn();
     if (encode == nullptr) MAS_FUSED_NO("no cuTensorMapEncodeTiled");
     if (workspace == nullptr || workspace_bytes < fused_workspace_bytes(B, D, T_x, T_y)) return MAS_ERR_WORKSPACE_TOO_SMALL;
@@ -121,46 +120,38 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
         MAS_CUDA_TRY(cudaDeviceGetAttribute(&num_sms_cached[dev], cudaDevAttrMultiProcessorCount, dev));
     }
     const int max_smem = max_smem_cached[dev] - 2048;
-    const int half_smem = (max_smem_cached[dev] + 1024) / 2 - 2048;   // two CTAs per SM (1 KB reserved per CTA)
+    const int num_sms = num_sms_cached[dev];
 
-    // producers: token tiles of at most 112 tokens (28 groups of 4 -> 224 threads)
+    // a sweep CTA per utterance on its own SM, the other SMs produce; past a third of the SMs the
+    // producers become the long pole and two full-width launches are faster
     Geometry g{};
-    g.row_tiles = ceil_div(T_x, 112);
-    g.tile_rows = ceil_div(ceil_div(T_x, g.row_tiles), 8) * 8;
-    g.nchunks = ceil_div(T_y, kGemmFrames);
-    const int gemm_smem = logp::cta_smem_floats(D, g.tile_rows) * 4;
+    g.t = make_tile_shape(T_x, T_y);
+    const int BT = B * g.t.row_tiles;
+    g.P = num_sms - B;
+    if (3 * B > num_sms || BT > g.P) MAS_FUSED_NO("too many utterances for one wave");
+    g.deal = logp::make_deal(g.P, BT, g.t.nchunks);
+    const int gemm_smem = logp::cta_smem_floats(D, g.t) * 4;
+    if (gemm_smem > max_smem) MAS_FUSED_NO("shared memory (producers)");
 
-    // sweep CTAs: K = 1, deepest ring that still lets two CTAs share an SM, else one per SM
+    // sweep CTAs: K = 1, deepest ring that fits
     systolic::Plan plan{};
-    bool ok = false, two_per_sm = false;
-    for (int pass = 0; pass < 2 && !ok; ++pass) {
-        const int budget = pass == 0 ? half_smem : max_smem;
-        if (gemm_smem > budget) continue;
-        for (int bits_smem = 1; bits_smem >= 0 && !ok; --bits_smem)
-            for (int S = 4; S >= 2 && !ok; --S) {
-                plan = systolic::make_plan(R, W, S, 1, T_y, bits_smem != 0, 8192);
-                if (plan.total <= budget) {
-                    ok = true;
-                    two_per_sm = pass == 0;
-                }
-            }
-    }
-    if (!ok) MAS_FUSED_NO("shared memory");
-    const int smem_bytes = gemm_smem > plan.total ? gemm_smem : plan.total;
-    const int64_t slots = (int64_t)num_sms_cached[dev] * (two_per_sm ? 2 : 1);
-    int64_t n_per = (slots - B) / ((int64_t)B * g.row_tiles);
-    if (n_per < 1) n_per = 1;
-    if (n_per > g.nchunks) n_per = g.nchunks;
-    g.n_per = (int)n_per;
-    g.n_gemm = B * g.row_tiles * g.n_per;
+    bool ok = false;
+    for (int bits_smem = 1; bits_smem >= 0 && !ok; --bits_smem)
+        for (int S = 4; S >= 2 && !ok; --S) {
+            plan = systolic::make_plan(R, W, S, 1, T_y, bits_smem != 0, 8192);
+            ok = plan.total <= max_smem;
+        }
+    if (!ok) MAS_FUSED_NO("shared memory (sweep)");
+    int smem_bytes = gemm_smem > plan.total ? gemm_smem : plan.total;
+    const int solo = (max_smem_cached[dev] + 1024) / 2;                 // more than half an SM: one CTA per SM
+    if (smem_bytes < solo) smem_bytes = solo;
 
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     float *scores = reinterpret_cast<float *>(ws);
     ws += align_up((size_t)B * T_x * T_y * 4, 256);
     g.ready = reinterpret_cast<int *>(ws);
-    g.queue = g.ready + (size_t)B * g.nchunks;
     ws += fused_flag_bytes(B, T_y);
-    MAS_CUDA_TRY(cudaMemsetAsync(g.ready, 0, (size_t)B * (g.nchunks + g.row_tiles) * 4, stream));
+    MAS_CUDA_TRY(cudaMemsetAsync(g.ready, 0, (size_t)B * g.t.nchunks * 4, stream));
 
     LogpParams lp = lp_in;
     lp.logp = scores;
@@ -189,8 +180,8 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) MAS_FUSED_NO("tensor map encode failed");
     if (debug)
-        fprintf(stderr, "[mas_b200] single launch: %d producers (%d per tile, %d tiles of %d tokens) + %d sweep CTAs, %d B smem, R=%d W=%d S=%d\n",
-                g.n_gemm, g.n_per, g.row_tiles, g.tile_rows, B, smem_bytes, plan.R, plan.W, plan.S);
+        fprintf(stderr, "[mas_b200] single launch: %d producers (%d per tile + %d spares, cover %d of %d chunks of %d frames, tiles of %d tokens) + %d sweep CTAs, %d B smem, R=%d W=%d S=%d\n",
+                g.P, g.deal.d, g.deal.spares, g.deal.cover, g.t.nchunks, g.t.F, g.t.tile_rows, B, smem_bytes, plan.R, plan.W, plan.S);
 
     switch (plan.R) {
         case 1: return launch_r<1>(tmap, pp, plan, lp, g, smem_bytes, stream);

@@ -1,7 +1,10 @@
 // mas_logp_cta.cuh -- the per-CTA program of the log-likelihood contraction (models.py:362-376):
-// one tile of tokens of one utterance, a list of 64-frame chunks.  Shared by the materialising
+// one tile of tokens of one utterance, a list of F-frame chunks.  Shared by the materialising
 // kernel (mas_logp.cu) and the fused launch (mas_fused.cu), where it also raises a ready flag per
 // chunk for the sweep CTAs.  Needs T_y % 4 == 0, 16-byte aligned z / logp rows, D <= 80.
+//
+// Also here: how the (utterance, token tile, chunk) units are dealt to P persistent CTAs
+// (struct Deal), the same for both kernels.
 #pragma once
 
 #include "mas_kernels.cuh"
@@ -14,22 +17,25 @@ namespace logp {
 constexpr int kPanel = 80;          // channels resident in shared memory at a time
 
 // floats of shared memory the program needs
-__host__ __device__ inline int cta_smem_floats(int D, int tile_rows) {
-    return 2 * D * tile_rows + 2 * D * kGemmFrames + 2 * tile_rows + kGemmFrames;
+__host__ __device__ inline int cta_smem_floats(int D, const TileShape &t) {
+    return 2 * D * t.tile_rows + 2 * D * t.F + 2 * t.tile_rows + t.F;
 }
 
-// chunks chunk_first, chunk_first + chunk_stride, ... (chunk_count of them, < nchunks)
+// chunks chunk_first, chunk_first + chunk_stride, ... (chunk_count of them) of token tile x0 of
+// utterance b; indices from skip_from up are shifted by skip_by (the chunks the spare CTAs take)
 template <bool kSignal>
-__device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int tile_rows, int b, int x0, int chunk_first,
-                                         int chunk_stride, int chunk_count, int *ready, long long *dbg_ns = nullptr,
-                                         int *queue = nullptr, int nchunks = 0) {
+__device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, const TileShape &t, int b, int x0, int chunk_first,
+                                         int chunk_stride, int chunk_count, int skip_from, int skip_by, int *ready,
+                                         long long *dbg_ns = nullptr) {
+    if (chunk_count <= 0) return;
     const int D = p.D, T_x = p.T_x, T_y = p.T_y;
+    const int tile_rows = t.tile_rows, F = t.F, CG = t.CG;
     float *sInv = sm;                                   // [D][tile_rows]
     float *sMiv = sInv + D * tile_rows;                 // [D][tile_rows]
-    float *sZ = sMiv + D * tile_rows;                   // [2][D][64]  (double-buffered chunk of z)
-    float *sL1 = sZ + 2 * D * kGemmFrames;              // [tile_rows]
+    float *sZ = sMiv + D * tile_rows;                   // [2][D][F]  (double-buffered chunk of z)
+    float *sL1 = sZ + 2 * D * F;                        // [tile_rows]
     float *sL4 = sL1 + tile_rows;                       // [tile_rows]
-    float *sL2 = sL4 + tile_rows;                       // [64] mean_only: per-frame sum of -0.5 z^2
+    float *sL2 = sL4 + tile_rows;                       // [F] mean_only: per-frame sum of -0.5 z^2
     const bool mean_only = p.x_logs == nullptr;         // config.py:52, the reference default
 
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -37,50 +43,44 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
     const float *xl = p.x_logs ? p.x_logs + (int64_t)b * D * T_x : nullptr;
     const float *zg = p.z + (int64_t)b * D * T_y;
     float *out = p.logp + (int64_t)b * T_x * T_y;
-    const int rg = tid >> 3, cg = tid & 7;              // kGemmTM tokens x {4+4} frames per thread
-    const bool worker = rg * kGemmTM < tile_rows;
+    const int rg = tid / CG, cg = tid - rg * CG;        // 4 tokens x {4+4} frames per thread
+    const bool worker = rg < t.RG;
+    const int f4 = F >> 2;                              // 16-byte pieces per chunk row
 
     auto stage_frames_async = [&](int ch, int buf) {
-        const int y0 = ch * kGemmFrames;
-        float *dst = sZ + buf * D * kGemmFrames;
-        for (int i = tid; i < D * (kGemmFrames / 4); i += nthr) {
-            const int d = i >> 4, y = y0 + ((i & 15) << 2);
+        const int y0 = ch * F;
+        float *dst = sZ + buf * D * F;
+        for (int i = tid; i < D * f4; i += nthr) {
+            const int d = i / f4, y = y0 + ((i - d * f4) << 2);
             ptx::cp_async_16(dst + (i << 2), zg + (int64_t)d * T_y + (y < T_y ? y : 0), y < T_y);
         }
         ptx::cp_async_commit();
     };
 
-    // Chunk order: a fixed arithmetic sequence, or (queue != null) whatever this tile's shared counter
-    // hands out next -- CTAs that share their SM with a sweep CTA then simply take fewer chunks.
-    __shared__ int s_next;
-    auto take = [&]() -> int {                          // every thread gets the same answer
-        __syncthreads();
-        if (tid == 0) s_next = atomicAdd(queue, 1);
-        __syncthreads();
-        return s_next;
+    // the sequence is kept in un-shifted numbering; `ch` is the real chunk
+    int seq = chunk_first;
+    auto next_chunk = [&](int) {
+        seq += chunk_stride;
+        return seq >= skip_from ? seq + skip_by : seq;
     };
-    int ch = chunk_first, ch_next = 0;
-    if (queue != nullptr) {
-        ch = take();
-        if (ch >= nchunks) return;
-        chunk_count = nchunks;                          // upper bound; the loop ends when the queue is dry
-    } else if (chunk_count <= 0) {
-        return;
-    }
+    __syncthreads();                                    // a previous tile of this CTA is done with the shared memory
+    int ch = seq >= skip_from ? seq + skip_by : seq;
     if (dbg_ns && tid == 0) dbg_ns[0] = ptx::globaltimer_ns();
     stage_frames_async(ch, 0);                          // in flight while the token side is prepared
     // token side: thread (x, h) stages token x0+x for one contiguous share of the channels (coalesced
-    // over x, eight loads in flight) and sums its share of the row constants, channels ascending;
-    // the shares are then added in order.  nsh = how many threads serve a token (2 at 224 / 112).
+    // over x) and sums its share of the row constants, channels ascending; the shares are then added
+    // in order.  nsh = how many threads serve a token (2 at 512 / 200).  The loop is kept SMALL: this
+    // is cold code that every warp runs once, and unrolled by 20 it was bound by instruction fetch
+    // (stall_no_inst, profiles/r1_ncu_logp.txt), not by the loads.
     const int nsh = max(1, min(4, nthr / tile_rows));
     const int dsh = ceil_div(D, nsh);
-    float *sPart = sZ + D * kGemmFrames;                // buffer 1 of sZ is still free: [nsh][2][tile_rows]
+    float *sPart = sZ + D * F;                          // buffer 1 of sZ is still free: [nsh][2][tile_rows]
     if (tid < nsh * tile_rows) {
         const int h = tid / tile_rows, x = tid - h * tile_rows, xg = x0 + x;
         const int d0 = h * dsh, d1 = min(D, d0 + dsh);
         float l1 = 0.f, l4 = 0.f;
         if (xg < T_x) {
-#pragma unroll 8
+#pragma unroll 4
             for (int d = d0; d < d1; ++d) {
                 const float m = __ldg(xm + (int64_t)d * T_x + xg);
                 const float ls = xl ? __ldg(xl + (int64_t)d * T_x + xg) : 0.f;
@@ -107,32 +107,34 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
         sL4[tid] = l4;
     }
     __syncthreads();                                    // sPart is read before chunk 1 lands in that buffer
-    float acc[kGemmTM][8];
+    if (dbg_ns && tid == 0) dbg_ns[8] = ptx::globaltimer_ns();
+    GemmAcc acc;
+    // One CTA barrier per chunk: it makes chunk k's frames visible, says that every warp is done with
+    // chunk k-1 (its frame buffer may be refilled, its scores are stored), and orders those stores
+    // before thread 0's release of chunk k-1's flag.
+    int ch_prev = ch;
     for (int k = 0; k < chunk_count; ++k) {
         const int buf = k & 1;
-        bool more;
-        if (queue != nullptr) {
-            ch_next = take();
-            more = ch_next < nchunks;
-        } else {
-            ch_next = ch + chunk_stride;
-            more = k + 1 < chunk_count;
+        const int ch_next = next_chunk(ch);
+        const bool more = k + 1 < chunk_count;
+        ptx::cp_async_wait<0>();
+        __syncthreads();
+        if (kSignal && k > 0 && tid == 0) {
+            __threadfence();                            // the CTA's scores (ordered by the barrier) before the flag
+            ptx::red_release_gpu_add(ready + ch_prev, 1);
+            if (dbg_ns) dbg_ns[k < 8 ? k : 7] = ptx::globaltimer_ns();
         }
-        if (more) {
-            stage_frames_async(ch_next, buf ^ 1);       // buffer buf^1 was released by the barrier below
-            ptx::cp_async_wait<1>();
-        } else {
-            ptx::cp_async_wait<0>();
-        }
-        __syncthreads();                                // chunk ch (and the token side) visible to everyone
+        if (dbg_ns && tid == 0 && k < 3) dbg_ns[12 + k] = ptx::globaltimer_ns();
+        if (dbg_ns && tid == 0 && k == 0) dbg_ns[5] = clock64();
+        if (more) stage_frames_async(ch_next, buf ^ 1); // lands while this chunk is contracted
         if (mean_only) {
             // inv_var == 1: the inv_var term does not depend on the token (models.py:367-369 with
             // x_logs == 0): one sum per frame, channels ascending
-            if (tid < kGemmFrames) {
-                const float *zc = sZ + buf * D * kGemmFrames + tid;
+            if (tid < F) {
+                const float *zc = sZ + buf * D * F + tid;
                 float l2 = 0.f;
                 for (int d = 0; d < D; ++d) {
-                    const float zv = zc[d * kGemmFrames];
+                    const float zv = zc[d * F];
                     l2 = fmaf(-0.5f * zv, zv, l2);
                 }
                 sL2[tid] = l2;
@@ -141,10 +143,12 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
         }
         if (worker) {
             if (mean_only)
-                gemm_tile<kGemmTM, true, true>(sInv, sMiv, sZ + buf * D * kGemmFrames, D, tile_rows, rg, cg, acc);
+                gemm_tile<true, true>(sInv, sMiv, sZ + buf * D * F, D, tile_rows, F, rg, cg, acc);
             else
-                gemm_tile<kGemmTM, true, false>(sInv, sMiv, sZ + buf * D * kGemmFrames, D, tile_rows, rg, cg, acc);
-            const int y0 = ch * kGemmFrames;
+                gemm_tile<true, false>(sInv, sMiv, sZ + buf * D * F, D, tile_rows, F, rg, cg, acc);
+            if (dbg_ns && tid == 0 && k < 3) dbg_ns[9 + k] = ptx::globaltimer_ns();
+            if (dbg_ns && tid == 0 && k == 0) dbg_ns[6] = clock64();
+            const int y0 = ch * F;
 #pragma unroll
             for (int i = 0; i < kGemmTM; ++i) {
                 const int xr = rg * kGemmTM + i, x = x0 + xr;
@@ -153,34 +157,126 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, int til
                 float *row = out + (int64_t)x * T_y;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int y = y0 + 32 * h + 4 * cg;
+                    const int yl = (F >> 1) * h + 4 * cg, y = y0 + yl;
                     if (y < T_y) {                      // T_y % 4 == 0: whole float4 or nothing
+                        float c[4];
+                        acc.quad(i, h, c);
                         float4 r;
                         if (mean_only) {
-                            const float4 l2 = *reinterpret_cast<const float4 *>(sL2 + 32 * h + 4 * cg);
-                            r.x = logp_cell_finish_mean_only(l1, l2.x, acc[i][4 * h + 0], l4);
-                            r.y = logp_cell_finish_mean_only(l1, l2.y, acc[i][4 * h + 1], l4);
-                            r.z = logp_cell_finish_mean_only(l1, l2.z, acc[i][4 * h + 2], l4);
-                            r.w = logp_cell_finish_mean_only(l1, l2.w, acc[i][4 * h + 3], l4);
+                            const float4 l2 = *reinterpret_cast<const float4 *>(sL2 + yl);
+                            r.x = logp_cell_finish_mean_only(l1, l2.x, c[0], l4);
+                            r.y = logp_cell_finish_mean_only(l1, l2.y, c[1], l4);
+                            r.z = logp_cell_finish_mean_only(l1, l2.z, c[2], l4);
+                            r.w = logp_cell_finish_mean_only(l1, l2.w, c[3], l4);
                         } else {
-                            r.x = logp_cell_finish(l1, acc[i][4 * h + 0], l4);
-                            r.y = logp_cell_finish(l1, acc[i][4 * h + 1], l4);
-                            r.z = logp_cell_finish(l1, acc[i][4 * h + 2], l4);
-                            r.w = logp_cell_finish(l1, acc[i][4 * h + 3], l4);
+                            r.x = logp_cell_finish(l1, c[0], l4);
+                            r.y = logp_cell_finish(l1, c[1], l4);
+                            r.z = logp_cell_finish(l1, c[2], l4);
+                            r.w = logp_cell_finish(l1, c[3], l4);
                         }
                         *reinterpret_cast<float4 *>(row + y) = r;
                     }
                 }
             }
-            if (kSignal) __threadfence();               // this thread's scores before the flag below
         }
-        __syncthreads();                                // everyone is done with buffer buf (and has stored)
-        if (kSignal && tid == 0) {
-            ptx::red_release_gpu_add(ready + ch, 1);
-            if (dbg_ns) dbg_ns[k < 15 ? k + 1 : 15] = ptx::globaltimer_ns();
-        }
-        if (!more) break;
+        ch_prev = ch;
         ch = ch_next;
+    }
+    __syncthreads();                                    // everyone has stored the last chunk
+    if (kSignal && tid == 0) {
+        __threadfence();
+        ptx::red_release_gpu_add(ready + ch_prev, 1);
+        if (dbg_ns) dbg_ns[chunk_count < 8 ? chunk_count : 7] = ptx::globaltimer_ns();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dealing the work to P persistent CTAs.  A "row" is one token tile of one utterance (BT = B x
+// row_tiles of them), with nchunks chunks each; staging a row's token side costs about a third of a
+// chunk, so a CTA should stay on its row.
+//   * whole passes while rows outnumber CTAs: CTA p takes rows p, p + P, ... with all their chunks;
+//   * the remaining `rem` rows (rem <= P) get d = P / rem dedicated CTAs each, CTA j of a row taking
+//     chunks j, j + d, ... below `cover` -- so the scores of EARLY frames of every utterance exist
+//     first, which is what the sweep CTAs of the fused launch wait for;
+//   * when that would need one round more than the work justifies, `nchunks - cover` chunks per row
+//     are dealt one at a time to the P - d rem spare CTAs instead: chunks [spare_first, spare_first +
+//     nchunks - cover), taken from just before the dedicated CTAs' last round when the spares are
+//     done by then (the last round then ends with the final, usually narrower, chunk and the sweep
+//     has less left to do after it), else from the end.
+//     (200 x 1000, 32 utterances, 116 producers: 3 dedicated CTAs x 4 rounds take chunks 0-8 and
+//     10-12, 20 spares take the 32 chunks number 9.)
+// ---------------------------------------------------------------------------------------------
+struct Deal {
+    int P, BT, nchunks;
+    int passes;        // whole passes over P rows
+    int rem;           // rows of the last, partial pass
+    int d;             // dedicated CTAs per remaining row
+    int cover;         // chunks the dedicated CTAs take per row; nchunks - cover go to the spares
+    int spare_first;   // first chunk of the spares' range
+    int spares;
+};
+
+inline Deal make_deal(int P, int BT, int nchunks) {
+    Deal q{};
+    q.P = P;
+    q.BT = BT;
+    q.nchunks = nchunks;
+    q.passes = BT / P;
+    q.rem = BT - q.passes * P;
+    q.d = 0;
+    q.cover = nchunks;
+    q.spare_first = nchunks;
+    q.spares = 0;
+    if (q.rem == 0) return q;
+    q.d = P / q.rem;
+    if (q.d > nchunks) q.d = nchunks;
+    q.spares = P - q.d * q.rem;
+    // rounds if the dedicated CTAs do everything, against a cover that leaves the tail to the spares
+    const int all = ceil_div(nchunks, q.d);
+    if (q.spares > 0 && all > 1) {
+        const int cover = q.d * (all - 1);                                 // one round less
+        const int left = (nchunks - cover) * q.rem;                        // units for the spares
+        const double spare_rounds = ceil_div(left, q.spares) * 1.35;       // each restages its token side
+        if (spare_rounds <= all - 1) {
+            q.cover = cover;
+            q.spare_first = (spare_rounds <= all - 2) ? cover - q.d : cover;
+        }
+    }
+    return q;
+}
+
+// Runs CTA `pidx`'s share.  ready: [B][nchunks] counters (kSignal only).  One call site of logp_cta:
+// the program is a few thousand instructions and instruction fetch is not free.
+template <bool kSignal>
+__device__ __forceinline__ void run_deal(const LogpParams &p, float *sm, const TileShape &t, const Deal &q, int pidx, int *ready,
+                                         long long *dbg_ns = nullptr) {
+    const int base = q.passes * q.P, dedicated = q.d * q.rem, per_row = q.nchunks - q.cover, left = per_row * q.rem;
+    for (int it = 0;; ++it) {
+        int r, first, stride = 1, count = 1, skip_from = 0x7fffffff;
+        if (it < q.passes) {                            // a whole row
+            r = it * q.P + pidx;
+            first = 0;
+            count = q.nchunks;
+        } else if (q.rem == 0) {
+            break;
+        } else if (pidx < dedicated) {                  // dedicated CTA j of a remaining row
+            if (it > q.passes) break;
+            const int rr = pidx / q.d, j = pidx - rr * q.d;
+            r = base + rr;
+            first = j;
+            stride = q.d;
+            count = (q.cover - j + q.d - 1) / q.d;
+            skip_from = q.spare_first;                  // (== cover or beyond when the spares take the end)
+        } else {                                        // spare: one left-over chunk at a time
+            const int u = (pidx - dedicated) + (it - q.passes) * q.spares;
+            if (u >= left) break;
+            const int l = u / q.rem;
+            r = base + (u - l * q.rem);
+            first = q.spare_first + l;
+        }
+        const int b = r / t.row_tiles, rt = r - b * t.row_tiles;
+        logp_cta<kSignal>(p, sm, t, b, rt * t.tile_rows, first, stride, count, skip_from, per_row,
+                          kSignal ? ready + (size_t)b * q.nchunks : nullptr, dbg_ns);
     }
 }
 

@@ -36,7 +36,19 @@ prod = d[B * 16:]
 prod = prod[prod[:, 0] > 0]
 t0 = min(prod[:, 0].min(), dp[:, 0, 11].min())
 print(f"{len(prod)} producer CTAs, {B} sweep CTAs; times in us from the first stamp")
-for k in range(1, 16):
+names = {8: "token side staged", 9: "contraction #1 done", 10: "contraction #2 done", 11: "contraction #3 done",
+         12: "chunk #1 operands visible", 13: "chunk #2 operands visible", 14: "chunk #3 operands visible"}
+start = prod[:, 0]
+print(f"  producers start    {np.median(start - t0) / 1e3:7.1f}")
+for k in sorted(names):
+    col = prod[:, k]
+    ok = col > 0
+    if ok.any():
+        print(f"  producers: {names[k]:28s} {np.median(col[ok] - t0) / 1e3:7.1f}")
+cyc = (prod[:, 6] - prod[:, 5]).astype(float)
+ns = (prod[:, 9] - prod[:, 12]).astype(float)
+print(f"  producers: contraction #1 = {np.median(cyc):.0f} cycles in {np.median(ns) / 1e3:.2f} us -> {np.median(cyc / ns):.3f} GHz")
+for k in range(1, 5):
     col = prod[:, k]
     col = col[col > 0]
     if len(col):

@@ -123,3 +123,29 @@ def test_single_launch_equals_two_launches(pkg, oracle, shape, mean_only):
         assert torch.equal(a, b)
     logp = pkg.log_likelihood_matrix(*args[:3]).cpu().numpy()
     assert np.array_equal(one[0].cpu().numpy().astype(np.int32), oracle.maximum_path(logp, t_x, t_y))
+
+
+@pytest.mark.parametrize("shape", [
+    (32, 80, 200, 1000),    # C2: 4 dedicated CTAs per utterance + spares taking one chunk each
+    (160, 80, 40, 96),      # more token tiles than SMs: a whole pass, then a partial one
+    (5, 80, 300, 640),      # two token tiles per utterance
+    (3, 80, 257, 264),      # tile of 132 tokens, chunk count that does not divide
+    (2, 96, 50, 120),       # more than 80 channels: the panelled generic path
+    (2, 80, 50, 122),       # T_y % 4 != 0: the generic path
+    (1, 80, 7, 8),
+])
+def test_logp_every_unit_dealt_once(pkg, oracle, shape):
+    """Every (utterance, token tile, chunk) unit must be produced exactly once whatever the deal of
+    units to persistent CTAs: the output buffer is pre-filled with NaN, the scores are checked
+    against the fp64 formula."""
+    B, D, T_x, T_y = shape
+    rng = np.random.default_rng(zlib.crc32(repr(shape).encode()))
+    t_x, t_y = np.full(B, T_x, np.int32), np.full(B, T_y, np.int32)
+    for mean_only in (False, True):
+        x_m, x_logs, z = synth_prior(rng, B, D, T_x, T_y, t_x, t_y, mean_only, trained_like=False)
+        out = torch.full((B, T_x, T_y), float("nan"), device=DEV)
+        got = pkg.log_likelihood_matrix(to_dev(x_m), to_dev(x_logs), to_dev(z), out=out).cpu().numpy()
+        assert np.isfinite(got).all()
+        ref64 = oracle.logp_f64(x_m, x_logs, z)
+        rel = np.max(np.abs(got - ref64) / np.abs(ref64))
+        assert rel < LOGP_RTOL, (mean_only, rel)
