@@ -33,7 +33,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor", "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max"]
 traffic = {}
-for tag in ("mas", "fused"):
+for tag in ("mas", "fused", "logp"):
     rep = src / f"{R}_prof_{tag}.ncu-rep"
     if not rep.exists():
         continue
@@ -57,7 +57,36 @@ for tag in ("mas", "fused"):
         x = float(c.replace(",", ""))
         return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
     traffic[tag] = mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
-json.dump({"c2": traffic.get("fused"), "c1": traffic.get("mas"), "fused_c2": traffic.get("fused"),
+    # where the warps' time goes, by code region: the hottest loop (by executed count) against the rest
+    srcpage = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--csv", "--print-source", "sass"],
+                             capture_output=True, text=True).stdout
+    srows = list(csv.reader(srcpage.splitlines()))
+    if len(srows) > 3 and "Source" in srows[1]:
+        sh = srows[1]
+        ia, cs, ce = sh.index("Source"), sh.index("# Samples"), sh.index("Instructions Executed")
+        st = [(i, x) for i, x in enumerate(sh) if x.startswith("stall_") and "Not Issued" not in x]
+        body = [x for x in srows[2:] if len(x) > ce]
+        mx = max(float(x[ce] or 0) for x in body)
+        hot = [i for i, x in enumerate(body) if float(x[ce] or 0) > 0.9 * mx]
+        lo, hi = min(hot), max(hot)
+        tot = sum(float(x[cs] or 0) for x in body)
+
+        def region(a, b):
+            d = collections.Counter()
+            for x in body[a:b]:
+                for i, n in st:
+                    d[n[6:]] += float(x[i] or 0)
+            return sum(float(x[cs] or 0) for x in body[a:b]), d
+
+        with open(out / f"{R}_ncu_{tag}.txt", "a") as f:
+            f.write(f"# warp-state samples by code region ({int(tot)} samples, {len(body)} SASS instructions)\n")
+            for name, (a, b) in {"hottest loop": (lo, hi + 1), "before it": (0, lo), "after it": (hi + 1, len(body))}.items():
+                n, d = region(a, b)
+                top = ", ".join(f"{k} {int(v)}" for k, v in d.most_common(5) if v > 0)
+                f.write(f"#   {name:13s} instr {a:5d}..{b - 1:5d}: {n / max(tot, 1):6.1%} of samples ({top})\n")
+            mix = collections.Counter((x[ia].split()[1] if x[ia].strip().startswith("@") else x[ia].split()[0]) for x in body[lo:hi + 1])
+            f.write("#   hottest loop instruction mix: " + ", ".join(f"{k} {v}" for k, v in mix.most_common(8)) + "\n")
+json.dump({"c2": traffic.get("fused"), "c1": traffic.get("mas"), "fused_c2": traffic.get("fused"), "logp_c2": traffic.get("logp"),
            "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, B=32 200x1000"},
           open(out / "traffic.json", "w"), indent=1)
 print(open(out / f"{R}_launches.txt").read())
