@@ -15,6 +15,7 @@ entry point raises.
 """
 from . import _lib, alignment, monotonic_align  # noqa: F401
 from .alignment import (  # noqa: F401
+    aligned_mle_loss,
     expand_prior,
     fused_maximum_path,
     log_durations,
@@ -30,6 +31,7 @@ __all__ = [
     "log_likelihood_matrix",
     "expand_prior",
     "log_durations",
+    "aligned_mle_loss",
     "monotonic_align",
     "alignment",
 ]

@@ -206,3 +206,68 @@ def log_durations(durations, x_lengths):
                                             _stream(durations.device))
     _lib.check(rc, "mas_b200_log_durations_f32")
     return out
+
+
+class _AlignedMleLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, x_m, x_logs, logdet, frame_token, durations, y_len):
+        lib = _lib.load()
+        B, D, T_y = z.shape
+        T_x = x_m.shape[2]
+        out = torch.empty(2, dtype=torch.float32, device=z.device)
+        ws = torch.empty(lib.mas_b200_mle_loss_workspace_bytes(B, T_y), dtype=torch.uint8, device=z.device)
+        with torch.cuda.device(z.device):
+            rc = lib.mas_b200_mle_loss_f32(z.data_ptr(), x_m.data_ptr(), _ptr(x_logs), frame_token.data_ptr(), _ptr(logdet),
+                                           y_len.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), B, D, T_x, T_y,
+                                           _stream(z.device))
+        _lib.check(rc, "mas_b200_mle_loss_f32")
+        ctx.save_for_backward(z, x_m, x_logs if x_logs is not None else z.new_empty(0), frame_token, durations, out)
+        ctx.has_logs = x_logs is not None
+        ctx.logdet_shape = None if logdet is None else logdet.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        z, x_m, x_logs, frame_token, durations, out = ctx.saved_tensors
+        x_logs = x_logs if ctx.has_logs else None
+        B, D, T_y = z.shape
+        T_x = x_m.shape[2]
+        need_z, need_m, need_logs, need_logdet = ctx.needs_input_grad[:4]
+        scale = (g.float() * out[1]).reshape(1).contiguous()            # stays on the device: no host sync
+        dz = torch.empty_like(z) if need_z else None
+        want_tokens = need_m or (need_logs and x_logs is not None)
+        dx_m = torch.empty_like(x_m) if want_tokens else None
+        dx_logs = torch.empty_like(x_logs) if (need_logs and x_logs is not None) else None
+        if need_z or want_tokens:
+            with torch.cuda.device(z.device):
+                rc = lib.mas_b200_mle_loss_backward_f32(z.data_ptr(), x_m.data_ptr(), _ptr(x_logs), frame_token.data_ptr(),
+                                                        durations.data_ptr(), scale.data_ptr(), _ptr(dz), _ptr(dx_m), _ptr(dx_logs),
+                                                        B, D, T_x, T_y, _stream(z.device))
+            _lib.check(rc, "mas_b200_mle_loss_backward_f32")
+        dlogdet = (-scale).expand(ctx.logdet_shape).clone() if (need_logdet and ctx.logdet_shape is not None) else None
+        return dz, (dx_m if need_m else None), dx_logs, dlogdet, None, None, None
+
+
+def aligned_mle_loss(z, x_m, x_logs, logdet, frame_token, durations, y_lengths):
+    """``mle_loss(z, z_m, z_logs, logdet, z_mask)`` (utils.py:14-23, train.py:124) for the aligned prior,
+    from the token-level ``x_m`` / ``x_logs`` [B,D,T_x] and the ``frame_token`` / ``durations`` the
+    alignment kernels emit -- ``z_m`` / ``z_logs`` (models.py:383-392) are never built.  ``z`` [B,D,T_y]
+    (already masked, as the decoder returns it), ``logdet`` [B] or None, ``x_logs`` None == zeros
+    (mean_only), ``y_lengths`` the frame counts behind ``z_mask``.  Scalar fp32, differentiable w.r.t.
+    ``z``, ``x_m``, ``x_logs`` and ``logdet``."""
+    B, D, T_x, T_y = _check_prior(x_m, x_logs, z)
+    if frame_token.dtype != torch.int32 or durations.dtype != torch.int32:
+        raise TypeError("frame_token and durations must be int32 (as fused_maximum_path returns them)")
+    if tuple(frame_token.shape) != (B, T_y) or tuple(durations.shape) != (B, T_x):
+        raise ValueError("frame_token must be [B, T_y] and durations [B, T_x]")
+    if B == 0 or D == 0 or T_x == 0 or T_y == 0:
+        raise ValueError("aligned_mle_loss needs a non-empty batch")
+    if logdet is not None:
+        _require_cuda(logdet, "logdet")
+        if logdet.numel() != B:
+            raise ValueError("logdet must have one entry per utterance")
+        logdet = logdet.float().contiguous()
+    y_len = y_lengths.to(device=z.device, dtype=torch.int32).contiguous()
+    return _AlignedMleLoss.apply(z.contiguous(), x_m.contiguous(), None if x_logs is None else x_logs.contiguous(), logdet,
+                                 frame_token.contiguous(), durations.contiguous(), y_len)

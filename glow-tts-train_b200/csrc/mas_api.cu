@@ -187,6 +187,33 @@ int mas_b200_log_durations_f32(const int32_t *durations, const int32_t *x_len, f
     return launch_logw(durations, x_len, logw, B, T_x, static_cast<cudaStream_t>(stream));
 }
 
+size_t mas_b200_mle_loss_workspace_bytes(int B, int T_y) {
+    if (B <= 0 || T_y <= 0) return 0;
+    return mle_loss_workspace_bytes(B, T_y);
+}
+
+int mas_b200_mle_loss_f32(const float *z, const float *x_m, const float *x_logs, const int32_t *frame_token, const float *logdet,
+                          const int32_t *y_len, float *loss_and_inv_denom, void *workspace, size_t workspace_bytes, int B, int D,
+                          int T_x, int T_y, mas_stream_t stream) {
+    if (B <= 0 || D <= 0 || T_x <= 0 || T_y <= 0) return MAS_ERR_INVALID_ARGUMENT;   // an empty batch has no mean
+    if (!shape_ok(B, T_x, T_y) || D > MAS_B200_MAX_CHANNELS) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (!z || !x_m || !frame_token || !y_len || !loss_and_inv_denom) return MAS_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < mle_loss_workspace_bytes(B, T_y)) return MAS_ERR_WORKSPACE_TOO_SMALL;
+    return launch_mle_loss(z, x_m, x_logs, frame_token, logdet, y_len, loss_and_inv_denom, workspace, B, D, T_x, T_y,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_mle_loss_backward_f32(const float *z, const float *x_m, const float *x_logs, const int32_t *frame_token,
+                                   const int32_t *durations, const float *scale, float *dz, float *dx_m, float *dx_logs, int B,
+                                   int D, int T_x, int T_y, mas_stream_t stream) {
+    if (B <= 0 || D <= 0 || T_x <= 0 || T_y <= 0) return MAS_ERR_INVALID_ARGUMENT;
+    if (!shape_ok(B, T_x, T_y) || D > MAS_B200_MAX_CHANNELS) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (!z || !x_m || !frame_token || !durations || !scale) return MAS_ERR_INVALID_ARGUMENT;
+    if (dx_logs && (!x_logs || !dx_m)) return MAS_ERR_INVALID_ARGUMENT;
+    return launch_mle_loss_backward(z, x_m, x_logs, frame_token, durations, scale, dz, dx_m, dx_logs, B, D, T_x, T_y,
+                                    static_cast<cudaStream_t>(stream));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-buffer entry: staging buffers are cached per device and grown on demand.
 // ---------------------------------------------------------------------------------------------

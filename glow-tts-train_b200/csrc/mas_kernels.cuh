@@ -41,6 +41,12 @@ void path_systolic_force_cluster(int k);   // testing hook: CTAs per utterance (
 int launch_expand_gather(const float *x, const int32_t *frame_token, float *z, int B, int D, int T_x, int T_y, cudaStream_t stream);
 int launch_expand_scatter(const float *dz, const int32_t *durations, float *dx, int B, int D, int T_x, int T_y, cudaStream_t stream);
 int launch_logw(const int32_t *durations, const int32_t *x_len, float *logw, int B, int T_x, cudaStream_t stream);
+size_t mle_loss_workspace_bytes(int B, int T_y);
+int launch_mle_loss(const float *z, const float *x_m, const float *x_logs, const int32_t *frame_token, const float *logdet,
+                    const int32_t *y_len, float *out2, void *workspace, int B, int D, int T_x, int T_y, cudaStream_t stream);
+int launch_mle_loss_backward(const float *z, const float *x_m, const float *x_logs, const int32_t *frame_token,
+                             const int32_t *durations, const float *scale, float *dz, float *dx_m, float *dx_logs, int B, int D,
+                             int T_x, int T_y, cudaStream_t stream);
 
 // developer profiling hook: when non-null, kernels stamp clock64() phase times into it
 extern long long *g_dbg_cycles;

@@ -149,6 +149,28 @@ int mas_b200_expand_prior_backward_f32(const float *dz, const int32_t *durations
 int mas_b200_log_durations_f32(const int32_t *durations, const int32_t *x_len, float *logw, int B, int T_x, mas_stream_t stream);
 
 /*
+ * the maximum-likelihood loss of the aligned prior, `mle_loss(z, z_m, z_logs,
+ * logdet, z_mask)` (glow_tts_train/utils.py:14-23, called at train.py:124), from the TOKEN-level prior
+ * and the frame->token map -- z_m / z_logs (models.py:383-392) are never materialised:
+ *   loss = (sum_{b,d,y} [logs + 0.5 exp(-2 logs) (z - m)^2] - sum_b logdet[b]) / (D sum_b y_len[b]) + 0.5 log(2 pi),
+ *   m = x_m[b,d,frame_token[b,y]], logs = x_logs[b,d,frame_token[b,y]] (0 where frame_token < 0, and
+ *   everywhere when x_logs == NULL).  logdet may be NULL.
+ * loss_and_inv_denom: 2 floats on the device: the loss and 1 / (D sum y_len) (what the backward scales by).
+ * backward: `scale` = DEVICE pointer to (upstream gradient) x (1 / denominator);
+ *   dz[b,d,y] = scale exp(-2 logs)(z - m);  dx_m[b,d,x] = -scale sum over x's frames of exp(-2 logs)(z - m);
+ *   dx_logs[b,d,x] = scale sum over x's frames of (1 - exp(-2 logs)(z - m)^2);  (d logdet[b] = -scale, left to the caller).
+ *   Any of dz / dx_m / dx_logs may be NULL (dx_logs needs x_logs and dx_m).
+ * Deterministic: fixed summation order.  z [B][D][T_y], x_m / x_logs [B][D][T_x] fp32 contiguous.
+ */
+size_t mas_b200_mle_loss_workspace_bytes(int B, int T_y);
+int mas_b200_mle_loss_f32(const float *z, const float *x_m, const float *x_logs, const int32_t *frame_token, const float *logdet,
+                          const int32_t *y_len, float *loss_and_inv_denom, void *workspace, size_t workspace_bytes, int B, int D,
+                          int T_x, int T_y, mas_stream_t stream);
+int mas_b200_mle_loss_backward_f32(const float *z, const float *x_m, const float *x_logs, const int32_t *frame_token,
+                                   const int32_t *durations, const float *scale, float *dz, float *dx_m, float *dx_logs, int B,
+                                   int D, int T_x, int T_y, mas_stream_t stream);
+
+/*
  * Host-buffer convenience used for end-to-end timing and by non-torch callers: takes HOST
  * pointers with the layout of maximum_path_c (core.pyx:40) -- values fp32 [B][T_x][T_y]
  * C-contiguous (NOT clobbered), t_xs / t_ys int32 [B], paths int32 [B][T_x][T_y] (fully written)

@@ -49,3 +49,54 @@ def test_consumers_match_reference_matmuls(pkg, shape):
     for b in range(B):
         assert gx[b, :, t_x[b]:].abs().sum() == 0
         assert z_m[b, :, t_y[b]:].abs().sum() == 0
+
+
+def reference_mle_loss(z, m, logs, logdet, mask):
+    """utils.py:14-23 verbatim (in whatever precision the arguments have)."""
+    import math
+    loss = torch.sum(logs) + 0.5 * torch.sum(torch.exp(-2 * logs) * ((z - m) ** 2))
+    loss = loss - torch.sum(logdet)
+    loss = loss / torch.sum(torch.ones_like(z) * mask)
+    loss = loss + 0.5 * math.log(2 * math.pi)
+    return loss
+
+
+@pytest.mark.parametrize("mean_only", [False, True])
+@pytest.mark.parametrize("shape", [(3, 80, 37, 150), (4, 80, 200, 1000), (2, 16, 5, 9), (1, 7, 1, 3)])
+def test_aligned_mle_loss_matches_reference(pkg, shape, mean_only):
+    """the loss and its gradients from the token-level prior equal the
+    reference's mle_loss on the expanded prior (evaluated in fp64 through the reference's own
+    matmul expansion and autograd)."""
+    B, D, T_x, T_y = shape
+    rng = np.random.default_rng(B * 977 + T_x + int(mean_only))
+    t_x, t_y = ragged_lengths(rng, B, T_x, T_y)
+    value = torch.from_numpy((10 * rng.standard_normal((B, T_x, T_y)) - 100).astype(np.float32)).to(DEV)
+    tx_d, ty_d = torch.from_numpy(t_x).to(DEV), torch.from_numpy(t_y).to(DEV)
+    path, dur, tok = pkg.maximum_path_from_lengths(value, tx_d, ty_d, want_durations=True, want_frame_token=True)
+    x_mask = (torch.arange(T_x, device=DEV)[None] < tx_d[:, None]).float().unsqueeze(1)
+    z_mask = (torch.arange(T_y, device=DEV)[None] < ty_d[:, None]).float().unsqueeze(1)
+    x_m = (torch.randn(B, D, T_x, device=DEV) * x_mask).requires_grad_(True)
+    x_logs = None if mean_only else ((0.3 * torch.randn(B, D, T_x, device=DEV) - 0.2) * x_mask).requires_grad_(True)
+    z = (torch.randn(B, D, T_y, device=DEV) * z_mask).requires_grad_(True)
+    logdet = torch.randn(B, device=DEV).requires_grad_(True)
+
+    loss = pkg.aligned_mle_loss(z, x_m, x_logs, logdet, tok, dur, ty_d)
+    inputs = [z, x_m, logdet] + ([] if mean_only else [x_logs])
+    grads = torch.autograd.grad(loss, inputs)
+
+    # the reference in fp64: dense-path matmuls (models.py:383-392) + mle_loss (utils.py:14-23)
+    z64, xm64, ld64 = (t.detach().double().requires_grad_(True) for t in (z, x_m, logdet))
+    xl64 = (torch.zeros_like(xm64) if mean_only else x_logs.detach().double()).requires_grad_(True)
+    attn = path.double().unsqueeze(1)
+    zm_ref, zl_ref, _ = reference_consumers(attn, xm64, xl64, x_mask.double())
+    loss_ref = reference_mle_loss(z64, zm_ref, zl_ref, ld64, z_mask.double())
+    grads_ref = torch.autograd.grad(loss_ref, [z64, xm64, ld64] + ([] if mean_only else [xl64]))
+
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    for name, g, r in zip(["z", "x_m", "logdet", "x_logs"], grads, grads_ref):
+        r = r.float()
+        assert g.shape == r.shape, name
+        assert torch.allclose(g, r, rtol=1e-4, atol=1e-6 * float(r.abs().max()) + 1e-12), (name, (g - r).abs().max().item())
+    # deterministic: a second evaluation gives the same bits
+    loss2 = pkg.aligned_mle_loss(z, x_m, x_logs, logdet, tok, dur, ty_d)
+    assert torch.equal(loss, loss2)
