@@ -155,6 +155,8 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
 
     LogpParams lp = lp_in;
     lp.logp = scores;
+    lp.x_len = x_len;
+    lp.y_len = y_len;
     PathParams pp{};
     pp.value = scores;
     pp.value_stride_b = (int64_t)T_x * T_y;

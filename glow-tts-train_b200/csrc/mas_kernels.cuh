@@ -27,6 +27,9 @@ struct LogpParams {
     const float *x_m, *x_logs, *z;  // x_logs nullable (mean_only)
     float *logp;
     int B, D, T_x, T_y;
+    // single launch only: the utterances' lengths.  Scores outside the reference's band
+    // (core.pyx:18) are never read by the sweep, so the producers do not contract them.
+    const int32_t *x_len = nullptr, *y_len = nullptr;
 };
 
 size_t path_simple_workspace_bytes(int B, int T_x, int T_y);

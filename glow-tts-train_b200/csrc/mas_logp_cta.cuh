@@ -45,6 +45,19 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, const T
     float *out = p.logp + (int64_t)b * T_x * T_y;
     const int rg = tid / CG, cg = tid - rg * CG;        // 4 tokens x {4+4} frames per thread
     const bool worker = rg < t.RG;
+    // Single launch: only the sweep reads these scores, and only inside the reference's band
+    // (core.pyx:18: max(0, t_x + y - t_y) <= x < min(t_x, y + 1)).  A thread whose four tokens are
+    // outside the band for every frame of the chunk skips the contraction and stores zeros (the
+    // sweep's boxes still cover those cells: they must be finite, their value is irrelevant);
+    // tokens beyond t_x and chunks more than a box past t_y are not touched at all.  With full
+    // lengths (200 x 1000) that is 15 % of the cells, with ragged batches whatever the padding is.
+    const bool banded = kSignal && p.x_len != nullptr;
+    int band_tx = T_x, band_ty = T_y;
+    if (banded) {
+        const Lengths len = clamp_lengths(p.x_len[b], p.y_len[b], T_x, T_y);
+        band_tx = len.tx;
+        band_ty = len.ty;
+    }
     const int f4 = F >> 2;                              // 16-byte pieces per chunk row
 
     auto stage_frames_async = [&](int ch, int buf) {
@@ -141,11 +154,23 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, const T
             }
             __syncthreads();
         }
-        if (worker) {
-            if (mean_only)
+        int mode = 2;                                   // 2: contract, 1: store zeros, 0: nothing
+        if (banded) {
+            const int y0 = ch * F, t0 = x0 + rg * kGemmTM;
+            const int lo = max(0, band_tx + y0 - band_ty), hi = min(band_tx, min(y0 + F, band_ty));
+            mode = (y0 >= band_ty + 32 || t0 >= band_tx) ? 0 : (t0 + kGemmTM > lo && t0 < hi) ? 2 : 1;
+        }
+        if (worker && mode != 0) {
+            if (mode == 1) {
+#pragma unroll
+                for (int i = 0; i < kGemmTM; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc.v[i][j] = 0ull;
+            } else if (mean_only) {
                 gemm_tile<true, true>(sInv, sMiv, sZ + buf * D * F, D, tile_rows, F, rg, cg, acc);
-            else
+            } else {
                 gemm_tile<true, false>(sInv, sMiv, sZ + buf * D * F, D, tile_rows, F, rg, cg, acc);
+            }
             if (dbg_ns && tid == 0 && k < 3) dbg_ns[9 + k] = ptx::globaltimer_ns();
             if (dbg_ns && tid == 0 && k == 0) dbg_ns[6] = clock64();
             const int y0 = ch * F;
@@ -162,7 +187,9 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, const T
                         float c[4];
                         acc.quad(i, h, c);
                         float4 r;
-                        if (mean_only) {
+                        if (mode == 1) {
+                            r = make_float4(0.f, 0.f, 0.f, 0.f);
+                        } else if (mean_only) {
                             const float4 l2 = *reinterpret_cast<const float4 *>(sL2 + yl);
                             r.x = logp_cell_finish_mean_only(l1, l2.x, c[0], l4);
                             r.y = logp_cell_finish_mean_only(l1, l2.y, c[1], l4);

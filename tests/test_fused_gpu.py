@@ -149,3 +149,24 @@ def test_logp_every_unit_dealt_once(pkg, oracle, shape):
         ref64 = oracle.logp_f64(x_m, x_logs, z)
         rel = np.max(np.abs(got - ref64) / np.abs(ref64))
         assert rel < LOGP_RTOL, (mean_only, rel)
+
+
+def test_single_launch_ignores_garbage_in_the_score_scratch(pkg, oracle):
+    """The producers of the single launch skip the cells outside the reference's band; whatever the
+    workspace held before (here: NaN, left in the caching allocator's block) must not reach the path."""
+    lib = pkg._lib.load()
+    B, D, T_x, T_y = 6, 80, 120, 520
+    rng = np.random.default_rng(77)
+    t_x, t_y = ragged_lengths(rng, B, T_x, T_y)
+    t_x[1], t_y[1] = 40, 80           # a short utterance: whole chunks beyond its last frame
+    t_x[2], t_y[2] = 1, 1
+    x_m, x_logs, z = synth_prior(rng, B, D, T_x, T_y, t_x, t_y, False)
+    args = (to_dev(x_m), to_dev(x_logs), to_dev(z), torch.from_numpy(t_x), torch.from_numpy(t_y))
+    for _ in range(2):
+        poison = torch.full((lib.mas_b200_fused_workspace_bytes(B, D, T_x, T_y) // 4 + 64,), float("nan"), device=DEV)
+        torch.cuda.synchronize()
+        del poison
+        path, dur = pkg.fused_maximum_path(*args)
+    logp = pkg.log_likelihood_matrix(*args[:3]).cpu().numpy()
+    assert np.array_equal(path.cpu().numpy().astype(np.int32), oracle.maximum_path(logp, t_x, t_y))
+    assert np.array_equal(dur.cpu().numpy(), path.cpu().numpy().sum(-1).astype(np.int32))
