@@ -18,7 +18,7 @@ constexpr int kPanel = 80;          // channels resident in shared memory at a t
 
 // floats of shared memory the program needs
 __host__ __device__ inline int cta_smem_floats(int D, const TileShape &t) {
-    return 2 * D * t.tile_rows + 2 * D * t.F + 2 * t.tile_rows + t.F;
+    return 2 * D * t.tile_rows + 2 * D * t.F + 2 * t.tile_rows + t.F + 8 * t.tile_rows;
 }
 
 // chunks chunk_first, chunk_first + chunk_stride, ... (chunk_count of them) of token tile x0 of
@@ -87,7 +87,7 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, const T
     // (stall_no_inst, profiles/r1_ncu_logp.txt), not by the loads.
     const int nsh = max(1, min(4, nthr / tile_rows));
     const int dsh = ceil_div(D, nsh);
-    float *sPart = sZ + D * F;                          // buffer 1 of sZ is still free: [nsh][2][tile_rows]
+    float *sPart = sL2 + F;                             // [nsh <= 4][2][tile_rows] partial row constants
     if (tid < nsh * tile_rows) {
         const int h = tid / tile_rows, x = tid - h * tile_rows, xg = x0 + x;
         const int d0 = h * dsh, d1 = min(D, d0 + dsh);
@@ -119,7 +119,7 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, const T
         sL1[tid] = l1;
         sL4[tid] = l4;
     }
-    __syncthreads();                                    // sPart is read before chunk 1 lands in that buffer
+    __syncthreads();
     if (dbg_ns && tid == 0) dbg_ns[8] = ptx::globaltimer_ns();
     GemmAcc acc;
     // One CTA barrier per chunk: it makes chunk k's frames visible, says that every warp is done with
