@@ -236,7 +236,7 @@ __device__ __forceinline__ int backtrack_tokens(const uint32_t *bits, int rows, 
                 w_up = *(p - rows);                         // same token, previous block
             } else {
                 w_left = (x > x_min) ? __ldcg(p - 1) : 0u;
-                w_up = (base > 0) ? __ldcg(p - rows) : 0u;
+                w_up = (x >= x_min && base > 0) ? __ldcg(p - rows) : 0u;
             }
             const bool alive = x >= x_min && base >= 0;
             const uint32_t m = alive ? (w & elig) : 0u;
@@ -245,7 +245,9 @@ __device__ __forceinline__ int backtrack_tokens(const uint32_t *bits, int rows, 
             const int y_lo = base + lo;
             if (step) run[x] = make_int2(y_lo, y_hi);
             y_hi = step ? y_lo - 1 : y_hi;
-            p = step ? p - 1 : p - rows;                    // (dead steps wander; nothing is dereferenced for use)
+            // dead steps (after the last token): stay put in global memory; in shared memory they may
+            // wander a few rows up -- nothing there is dereferenced for use, and it saves a select
+            p = step ? p - 1 : ((kSmem || alive) ? p - rows : p);
             elig = step ? (1u << lo) - 1u : 0xffffffffu;    // lo == 0: nothing left here, the next step goes up
             base -= (step || !alive) ? 0 : 32;
             x -= step ? 1 : 0;
