@@ -3,6 +3,8 @@
 // See mas_path_systolic.cu for the design notes.
 #pragma once
 
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -143,28 +145,32 @@ template <int R, bool kCluster>
 __device__ __forceinline__ void sweep_block(const float *__restrict__ tile, float (&v)[R], uint32_t (&acc)[R],
                                             float &carry, const float4 *__restrict__ bnd_in, uint32_t bnd_out,
                                             bool publisher, int lane) {
-    int swz[R];                                     // per-row XOR term of the 128B swizzle
-    const float *rowp[R];
+    // Shared-memory address of this lane's row i with its swizzle term folded in: rows are 128-byte
+    // aligned, so the 16-byte group g of row i sits at q[i] ^ (g << 4) -- one LOP3 with an immediate
+    // per load (the generic-pointer form took three instructions, and a lone warp pays ~2.3 cycles
+    // for each).
+    uint32_t q[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-        const int q = lane * R + i;
-        rowp[i] = tile + q * kBlk;
-        swz[i] = q & 7;
+        const int row = lane * R + i;
+        q[i] = ptx::smem_u32(tile + row * kBlk) ^ (uint32_t)((row & 7) << 4);
     }
+    const uint32_t bin = ptx::smem_u32(bnd_in);
     float4 LA[R], LB[R], bA, bB;
 #pragma unroll
-    for (int i = 0; i < R; ++i) LA[i] = *reinterpret_cast<const float4 *>(rowp[i] + (swz[i] << 2));
-    bA = bnd_in[0];
-#pragma unroll 1
+    for (int i = 0; i < R; ++i) LA[i] = ptx::ld_shared_v4(q[i]);
+    bA = ptx::ld_shared_v4(bin);
+#pragma unroll
     for (int g = 0; g < 8; g += 2) {
 #pragma unroll
-        for (int i = 0; i < R; ++i) LB[i] = *reinterpret_cast<const float4 *>(rowp[i] + (((g + 1) ^ swz[i]) << 2));
-        bB = bnd_in[g + 1];
+        for (int i = 0; i < R; ++i) LB[i] = ptx::ld_shared_v4(q[i] ^ (uint32_t)((g + 1) << 4));
+        bB = ptx::ld_shared_v4(bin + (g + 1) * 16);
         sweep_group<R, kCluster>(LA, bA, v, acc, carry, bnd_out, publisher, g);
-        const int gn = (g + 2) & 7;                 // the last prefetch wraps to group 0 and is discarded
+        if (g + 2 < 8) {
 #pragma unroll
-        for (int i = 0; i < R; ++i) LA[i] = *reinterpret_cast<const float4 *>(rowp[i] + ((gn ^ swz[i]) << 2));
-        bA = bnd_in[gn];
+            for (int i = 0; i < R; ++i) LA[i] = ptx::ld_shared_v4(q[i] ^ (uint32_t)((g + 2) << 4));
+            bA = ptx::ld_shared_v4(bin + (g + 2) * 16);
+        }
         sweep_group<R, kCluster>(LB, bB, v, acc, carry, bnd_out, publisher, g + 1);
     }
 }
@@ -357,7 +363,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         __syncthreads();
 
     long long *dbg = (kDbg && p.dbg_cycles && warp < 16) ? p.dbg_cycles + ((size_t)cta_tag * 16 + warp) * 16 : nullptr;
-    long long t_wait_prev = 0, t_wait_tma = 0, t_sweep = 0;
+    long long t_wait_prev = 0, t_wait_tma = 0, t_sweep = 0, t_core = 0;
     if (kDbg && dbg && lane == 0) dbg[0] = clock64();
     if (kDbg && dbg && tid == 0) dbg[11] = ptx::globaltimer_ns();
     int nonfinite = 0;
@@ -427,7 +433,9 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                     ptx::fence_proxy_async();               // these generic writes precede the TMA refill of the slot
                     __syncwarp();
                 }
+                const long long t4 = kDbg ? clock64() : 0;
                 sweep_block<R, kCluster>(tile, v, acc, carry, bin, bout, publisher, lane);
+                if (kDbg) t_core += clock64() - t4;
 #pragma unroll
                 for (int i = 0; i < R; ++i) acc[i] = __brev(acc[i]);   // first frame came in first: bit 31 -> bit 0
                 if (on_diagonal) {
@@ -479,6 +487,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
             dbg[2] = t_wait_prev;
             dbg[4] = t_wait_tma;
             dbg[8] = t_sweep;
+            dbg[9] = t_core;
             dbg[10] = cbend - cb0 + 1;
         }
     } else if (filler_warp) {
@@ -648,11 +657,11 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-// Tokens per lane (R) and sweep warps (W) for `tokens` tokens in one CTA.  A lone warp issues about
-// one instruction every two cycles, so the per-frame cost is ~2 x (4R + 5) cycles, and never below
-// the shuffle round trip amortised over R frames (~(29 + 10R)/R): R = 2..4 with at most one sweep
-// warp per scheduler is the sweet spot; longer texts take more tokens per lane first, more warps
-// second.
+// Tokens per lane (R) and sweep warps (W) for `tokens` tokens in one CTA.  The sweep is a chain of
+// (blocks + W - 1) steps; what a step costs was measured per R on B200 (profiles/sweep_k.py with
+// MAS_B200_FORCE_R, 32-frame blocks, cycles): the in-order warp eats one shuffle latency per frame
+// whatever R is, so two or three tokens per lane cost the same per step and three need fewer warps
+// (less skew); four is an outlier of nvcc's schedule and is only taken when nothing else fits.
 inline bool choose_shape(int tokens, int &R, int &W) {
     const int groups = ceil_div(tokens, kBlk);         // 32-token groups
     if (groups <= 1) {
@@ -660,16 +669,26 @@ inline bool choose_shape(int tokens, int &R, int &W) {
         W = 1;
         return true;
     }
-    for (int max_w : {4, 8, kMaxDpWarps})
-        for (int r : {2, 3, 4, 5, 6, 8}) {
-            const int w = ceil_div(groups, r);
-            if (w <= max_w) {
-                R = r;
-                W = w;
-                return true;
-            }
+    static const char *force_r = getenv("MAS_B200_FORCE_R");   // experiment hook
+    if (force_r != nullptr) {
+        R = atoi(force_r);
+        W = ceil_div(groups, R);
+        return R >= 1 && R <= 8 && R != 7 && W <= kMaxDpWarps;
+    }
+    static const int kR[] = {2, 3, 5, 6, 4, 8};
+    static const int kStep[] = {1950, 1955, 2130, 2500, 3100, 3400};
+    long best = -1;
+    for (int i = 0; i < 6; ++i) {
+        const int w = ceil_div(groups, kR[i]);
+        if (w > kMaxDpWarps) continue;
+        const long cost = (long)(40 + w - 1) * kStep[i];                 // ~40 blocks: a 1 300-frame utterance
+        if (best < 0 || cost < best) {
+            best = cost;
+            R = kR[i];
+            W = w;
         }
-    return false;
+    }
+    return best >= 0;
 }
 
 }  // namespace systolic

@@ -168,6 +168,11 @@ __device__ __forceinline__ void st_cluster_v4_if(bool pred, uint32_t addr, float
         ::"r"((uint32_t)pred), "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
         : "memory");
 }
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_shared_v4_if(bool pred, uint32_t addr, float4 v) {
     asm volatile(
         "{\n"

@@ -47,7 +47,7 @@ for w in range(16):
     sweep = np.median(d[:, w, 1] - d[:, w, 0])
     print(f"warp {w:2d}: start +{np.median(d[:, w, 0] - start):8.0f}  sweep/fill {sweep:9.0f} cyc   "
           f"wait prev {np.median(d[:, w, 2]):8.0f}  next {np.median(d[:, w, 3]):8.0f}  tma {np.median(d[:, w, 4]):8.0f}"
-          f"  | blocks {np.median(d[:, w, 10]):4.0f} compute {np.median(d[:, w, 8]):8.0f} tail {np.median(d[:, w, 9]):7.0f}")
+          f"  | blocks {np.median(d[:, w, 10]):4.0f} compute {np.median(d[:, w, 8]):8.0f} of which inside sweep_block {np.median(d[:, w, 9]):7.0f}")
 print(f"{len(d)} CTAs ({len(d) // B} per utterance)")
 print(f"CTA: barrier1 at +{np.median(d[:, 0, 5] - start):.0f}, backtrack {np.median(d[:, 0, 6] - d[:, 0, 5]):.0f} cyc, "
       f"end at +{np.median(d[:, 0, 7] - start):.0f} cyc")
