@@ -142,20 +142,16 @@ __device__ __forceinline__ void zero_below_diagonal(float *tile, int lane, int r
 // swept) and only unrolled twice: a DP warp runs alone on its scheduler, so nothing else hides a
 // shared-memory round trip or an instruction-cache miss.
 template <int R, bool kCluster>
-__device__ __forceinline__ void sweep_block(const float *__restrict__ tile, float (&v)[R], uint32_t (&acc)[R],
-                                            float &carry, const float4 *__restrict__ bnd_in, uint32_t bnd_out,
-                                            bool publisher, int lane) {
-    // Shared-memory address of this lane's row i with its swizzle term folded in: rows are 128-byte
-    // aligned, so the 16-byte group g of row i sits at q[i] ^ (g << 4) -- one LOP3 with an immediate
-    // per load (the generic-pointer form took three instructions, and a lone warp pays ~2.3 cycles
-    // for each).
+__device__ __forceinline__ void sweep_block(uint32_t tile, const uint32_t (&lane_c)[R], float (&v)[R], uint32_t (&acc)[R],
+                                            float &carry, uint32_t bin, uint32_t bnd_out, bool publisher) {
+    // tile: shared address of the staged box; lane_c[i] = this lane's row i inside it with its
+    // swizzle term folded in (rows are 128-byte aligned, so byte offset | swizzle): the 16-byte group g
+    // of row i sits at q[i] ^ (g << 4) -- one LOP3 with an immediate per load (the generic-pointer form
+    // took three instructions, and a lone warp pays ~2.3 cycles for each).  bin: the previous warp's
+    // boundary scores of this block.
     uint32_t q[R];
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
-        const int row = lane * R + i;
-        q[i] = ptx::smem_u32(tile + row * kBlk) ^ (uint32_t)((row & 7) << 4);
-    }
-    const uint32_t bin = ptx::smem_u32(bnd_in);
+    for (int i = 0; i < R; ++i) q[i] = tile + lane_c[i];
     float4 LA[R], LB[R], bA, bB;
 #pragma unroll
     for (int i = 0; i < R; ++i) LA[i] = ptx::ld_shared_v4(q[i]);
@@ -402,39 +398,53 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
             int seen_prev = (x0 > 0) ? -1 : kDoneAll;
             int seen_next = has_next ? -1 : kDoneAll;
             const bool lane0 = lane == 0, lane31 = lane == 31;
+            // every shared address the loop touches, as 32-bit shared-window addresses in registers
+            constexpr uint32_t kStage = rows_per_warp * kBlk * 4;
+            const uint32_t ring_a = ptx::smem_u32(my_ring), full_a = ptx::smem_u32(my_full), empty_a = ptx::smem_u32(my_empty);
+            const uint32_t bnd_in_a = ptx::smem_u32(bnd_in_base);
+            const uint32_t done_prev_a = ptx::smem_u32(&done[warp]), done_self_a = ptx::smem_u32(&done[1 + warp]),
+                           done_next_a = ptx::smem_u32(&done[warp + 2]);
+            uint32_t bits_a = ptx::smem_u32(bits_s + (size_t)cb0 * rows + (row0 - xc));   // advances one block row per block
+            uint32_t *bits_gp = bits_smem ? nullptr : bits_g + (size_t)cb0 * rows + (row0 - xc);
+            uint32_t lane_c[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int row = lane * R + i;
+                lane_c[i] = (uint32_t)(row * kBlk * 4) | (uint32_t)((row & 7) << 4);
+            }
 
             for (int cb = cb0; cb <= cbend; ++cb) {
                 uint32_t spins = 0;
                 const long long t0 = kDbg ? clock64() : 0;
                 while (seen_prev <= cb) {                       // previous warp has published block cb
-                    seen_prev = prev_remote ? ptx::ld_acquire_cluster_shared(&done[warp]) : ptx::ld_acquire_shared(&done[warp]);
+                    seen_prev = prev_remote ? ptx::ld_acquire_cluster_shared_a(done_prev_a) : ptx::ld_acquire_shared_a(done_prev_a);
                     if (++spins > kSpinLimit) spin_fail();
                 }
                 while (seen_next + kBndBlocks <= cb) {          // next warp has consumed block cb - ring depth
-                    seen_next = next_remote ? ptx::ld_acquire_cluster_shared(&done[warp + 2]) : ptx::ld_acquire_shared(&done[warp + 2]);
+                    seen_next = next_remote ? ptx::ld_acquire_cluster_shared_a(done_next_a) : ptx::ld_acquire_shared_a(done_next_a);
                     if (++spins > kSpinLimit) spin_fail();
                 }
                 const long long t2 = kDbg ? clock64() : 0;
-                while (!ptx::mbar_try_wait(&my_full[slot], parity))
+                const uint32_t slot8 = (uint32_t)slot * 8u;
+                while (!ptx::mbar_try_wait_a(full_a + slot8, parity))
                     if (++spins > kSpinLimit) spin_fail();
                 const long long t3 = kDbg ? clock64() : 0;
                 if (cb == cb0 && x0 > 0)                        // score of token x0-1 on the diagonal frame x0-1
-                    carry = bnd_in_base[((cb0 - 1) & (kBndBlocks - 1)) * kBlk + (kBlk - 1)];
+                    carry = ptx::ld_shared_f32_a(bnd_in_a + (uint32_t)((((cb0 - 1) & (kBndBlocks - 1)) * kBlk + (kBlk - 1)) * 4));
 
 #pragma unroll
                 for (int i = 0; i < R; ++i) acc[i] = 0u;
-                float *tile = my_ring + (size_t)slot * rows_per_warp * kBlk;
-                const float4 *bin = reinterpret_cast<const float4 *>(bnd_in_base + (cb & (kBndBlocks - 1)) * kBlk);
-                const uint32_t bout = bnd_out_base + (cb & (kBndBlocks - 1)) * kBlk * 4;
+                const uint32_t tile_a = ring_a + (uint32_t)slot * kStage;
+                const uint32_t ring_slot = (uint32_t)(cb & (kBndBlocks - 1)) * (kBlk * 4);
                 const int col0 = cb * kBlk;
                 const bool on_diagonal = cb < cb0 + R;        // warp-uniform
                 if (on_diagonal) {
-                    zero_below_diagonal<R>(tile, lane, row0, col0);
+                    zero_below_diagonal<R>(my_ring + (size_t)slot * rows_per_warp * kBlk, lane, row0, col0);
                     ptx::fence_proxy_async();               // these generic writes precede the TMA refill of the slot
                     __syncwarp();
                 }
                 const long long t4 = kDbg ? clock64() : 0;
-                sweep_block<R, kCluster>(tile, v, acc, carry, bin, bout, publisher, lane);
+                sweep_block<R, kCluster>(tile_a, lane_c, v, acc, carry, bnd_in_a + ring_slot, bnd_out_base + ring_slot, publisher);
                 if (kDbg) t_core += clock64() - t4;
 #pragma unroll
                 for (int i = 0; i < R; ++i) acc[i] = __brev(acc[i]);   // first frame came in first: bit 31 -> bit 0
@@ -448,10 +458,12 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                 }
                 if (bits_smem) {
 #pragma unroll
-                    for (int i = 0; i < R; ++i) bits_s[cb * rows + (row0 - xc) + i] = acc[i];
+                    for (int i = 0; i < R; ++i) ptx::st_shared_u32_a(bits_a + 4u * i, acc[i]);
+                    bits_a += (uint32_t)rows * 4u;
                 } else {
 #pragma unroll
-                    for (int i = 0; i < R; ++i) bits_g[(size_t)cb * rows + (row0 - xc) + i] = acc[i];
+                    for (int i = 0; i < R; ++i) bits_gp[i] = acc[i];
+                    bits_gp += rows;
                 }
                 // lane 31 wrote the boundary scores, so lane 31 publishes the progress (program order +
                 // release); remote mirrors first, the local counter last
@@ -459,9 +471,9 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                     ptx::st_release_cluster_if(lane31 && mirror_prev != 0u, mirror_prev, cb + 1);
                     ptx::st_release_cluster_if(lane31 && mirror_next != 0u, mirror_next, cb + 1);
                 }
-                ptx::st_release_shared_if(lane31, &done[1 + warp], cb + 1);
+                ptx::st_release_shared_if_a(lane31, done_self_a, cb + 1);
                 __syncwarp();                                  // every lane has read the box: hand the slot back
-                ptx::mbar_arrive_if(lane0, &my_empty[slot]);   // the loader warp refills it
+                ptx::mbar_arrive_if_a(lane0, empty_a + slot8);  // the loader warp refills it
                 if (++slot == S) {
                     slot = 0;
                     parity ^= 1u;

@@ -12,6 +12,61 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---- the same operations on 32-bit shared-window addresses ------------------------------------
+// (a lone sweep warp pays ~2.3 cycles per instruction: its block loop keeps every shared address it
+// needs in a register instead of re-deriving it from a generic pointer each time)
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_if_a(bool pred, uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %0, 0;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%1];\n"
+        "}\n"
+        ::"r"((uint32_t)pred), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ int ld_acquire_shared_a(uint32_t addr) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_acquire_cluster_shared_a(uint32_t addr) {
+    int v;
+    asm volatile("ld.acquire.cluster.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_shared_if_a(bool pred, uint32_t addr, int v) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %0, 0;\n"
+        "@p st.release.cta.shared.s32 [%1], %2;\n"
+        "}\n"
+        ::"r"((uint32_t)pred), "r"(addr), "r"(v)
+        : "memory");
+}
+__device__ __forceinline__ void st_shared_u32_a(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32_a(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // ---- mbarrier --------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
