@@ -21,13 +21,14 @@ __device__ __forceinline__ void cell(float &v, float adv, float l, uint32_t &acc
     acc = __funnelshift_l(__float_as_uint(diff), acc, 1);
 }
 
-template <int R, bool SKEW>
+template <int R, bool SKEW, bool SEL = true>
 __global__ void __launch_bounds__(32) sweep(float *out, int quads, long long *cyc, float l0) {
     const int lane = threadIdx.x;
     float v[R];
     uint32_t acc[R];
-    for (int i = 0; i < R; ++i) { v[i] = -1e9f; acc[i] = 0; }
-    float l[4] = {l0, l0 * 1.5f, l0 * 0.5f, l0 * 2.f};
+    for (int i = 0; i < R; ++i) { v[i] = -1e9f + lane; acc[i] = 0; }
+    const float ll = l0 + 1e-3f * lane;                 // lane-dependent: nothing here is warp-uniform
+    float l[4] = {ll, ll * 1.5f, ll * 0.5f, ll * 2.f};
     float up4[4] = {-1e9f, -1e9f, -1e9f, -1e9f};       // skewed: boundary values for this step
     const long long t0 = clock64();
     for (int q = 0; q < quads; ++q) {
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(32) sweep(float *out, int quads, long long *cy
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float up = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
-                if (lane == 0) up = -1e9f;
+                if (SEL && lane == 0) up = -1e9f;
 #pragma unroll
                 for (int i = R - 1; i >= 0; --i) cell(v[i], i == 0 ? up : v[i - 1], l[j] + i, acc[i]);
             }
@@ -58,14 +59,14 @@ __global__ void __launch_bounds__(32) sweep(float *out, int quads, long long *cy
     if (lane == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
 }
 
-template <int R, bool SKEW>
+template <int R, bool SKEW, bool SEL = true>
 void run(float *out, long long *cyc, const char *name) {
     const int quads = 4096;
     long long h = 0;
-    for (int rep = 0; rep < 2; ++rep) sweep<R, SKEW><<<148, 32>>>(out, quads, cyc, -3.f);
+    for (int rep = 0; rep < 2; ++rep) sweep<R, SKEW, SEL><<<148, 32>>>(out, quads, cyc, -3.f);
     cudaDeviceSynchronize();
     cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
-    printf("R=%d %-9s %6.1f cycles per frame  (%s)\n", R, name, (double)h / (4.0 * quads), cudaGetErrorString(cudaGetLastError()));
+    printf("R=%d %-28s %6.1f cycles per frame  (%s)\n", R, name, (double)h / (4.0 * quads), cudaGetErrorString(cudaGetLastError()));
 }
 
 int main() {
@@ -75,5 +76,6 @@ int main() {
     run<2, false>(out, cyc, "lockstep"); run<2, true>(out, cyc, "skewed");
     run<3, false>(out, cyc, "lockstep"); run<3, true>(out, cyc, "skewed");
     run<4, false>(out, cyc, "lockstep"); run<4, true>(out, cyc, "skewed");
+    run<2, false, false>(out, cyc, "lockstep, no lane-0 select"); run<3, false, false>(out, cyc, "lockstep, no lane-0 select");
     return 0;
 }
