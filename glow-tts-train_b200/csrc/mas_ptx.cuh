@@ -12,7 +12,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-// ---- the same operations on 32-bit shared-window addresses ------------------------------------
+// ---- synchronisation and loads/stores on 32-bit shared-window addresses -----------------------
 // (a lone sweep warp pays ~2.3 cycles per instruction: its block loop keeps every shared address it
 // needs in a register instead of re-deriving it from a generic pointer each time)
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
@@ -82,19 +82,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_if(bool pred, uint64_t *bar) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.u32 p, %0, 0;\n"
-        "@p mbarrier.arrive.shared::cta.b64 _, [%1];\n"
-        "}\n"
-        ::"r"((uint32_t)pred), "r"(smem_u32(bar))
-        : "memory");
-}
 // non-blocking probe of a phase
 __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -102,19 +89,6 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
@@ -130,22 +104,6 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-// Predicated "arm the barrier, then issue the box load": no branch, so a warp that runs alone on its
-// scheduler does not pay a divergent region just for lane 0 to talk to the TMA unit.
-__device__ __forceinline__ void tma_load_3d_if(bool pred, void *smem_dst, const CUtensorMap *map, uint64_t *bar,
-                                               uint32_t bytes, int c0, int c1, int c2) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.u32 p, %0, 0;\n"
-        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %4;\n"
-        "@p cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%1], [%2, {%5, %6, %7}], [%3];\n"
-        "}\n"
-        ::"r"((uint32_t)pred), "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
-          "r"(bytes), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void st_release_shared_if(bool pred, int *p, int v) {
@@ -183,15 +141,6 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// ---- acquire / release flags in shared memory -------------------------------------------------
-__device__ __forceinline__ int ld_acquire_shared(const int *p) {
-    int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_shared(int *p, int v) {
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
 
 // ---- thread-block clusters: rank, barrier, distributed shared memory ---------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -208,10 +157,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float4 v) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
 }
 __device__ __forceinline__ void st_cluster_v4_if(bool pred, uint32_t addr, float4 v) {
     asm volatile(
@@ -280,11 +225,6 @@ __device__ __forceinline__ void red_release_gpu_add(int *p, int v) {
 // generic-proxy writes (any state space) ordered before subsequent async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// ---- streaming (evict-first) 16-byte global store ---------------------------------------------
-__device__ __forceinline__ void st_global_cs_v4(float4 *p, float4 v) {
-    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-}
 
 }  // namespace ptx
 }  // namespace mas
