@@ -71,6 +71,12 @@ __device__ __forceinline__ f32x2 f32x2_fma(f32x2 a, f32x2 b, f32x2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+// acc += a * b in place: the same register pair in and out, so nvcc has nothing to rotate at the
+// loop's back edge (with separate operands it renamed the accumulators across the unrolled channels
+// and paid 16 moves per trip, most of them IMAD.MOV on the FMA pipe)
+__device__ __forceinline__ void f32x2_fma_acc(f32x2 &acc, f32x2 a, f32x2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ f32x2 f32x2_mul(f32x2 a, f32x2 b) {
     f32x2 d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -106,7 +112,7 @@ __device__ __forceinline__ void gemm_tile_d(const float *__restrict__ sInv, cons
     const float *pa = sInv + rg * TM, *pb = sMiv + rg * TM;
     const float *pz = sZ + cg * 4;
     const int half = F >> 1;
-#pragma unroll 2
+#pragma unroll 4
     for (int d = 0; d < D; ++d) {
         f32x2 av[TM], bv[TM];
         const float4 b = *reinterpret_cast<const float4 *>(pb);
@@ -129,12 +135,12 @@ __device__ __forceinline__ void gemm_tile_d(const float *__restrict__ sInv, cons
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc.v[i][j] = f32x2_fma(av[i], qv[j], acc.v[i][j]);
+                for (int j = 0; j < 4; ++j) f32x2_fma_acc(acc.v[i][j], av[i], qv[j]);
         }
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc.v[i][j] = f32x2_fma(bv[i], zv[j], acc.v[i][j]);
+            for (int j = 0; j < 4; ++j) f32x2_fma_acc(acc.v[i][j], bv[i], zv[j]);
     }
 }
 

@@ -1,5 +1,7 @@
 """Time the fused entry (single launch) vs the two kernels back to back, events around eager launches
-and around a CUDA graph of N steps:  python profiles/time_fused.py [B T_x T_y]"""
+and around a CUDA graph of N steps:  python profiles/time_fused.py [B T_x T_y] [--ragged]
+(--ragged: LJSpeech-like lengths as in SURVEY.md 8d -- t_x ~ U[T_x/2, T_x], t_y ~ t_x T_y/T_x U[0.8, 1.2],
+sorted by t_x descending, element 0 full size; times are per padded batch)"""
 import sys
 from pathlib import Path
 
@@ -10,7 +12,9 @@ import __graft_entry__ as entry  # noqa: E402
 
 pkg = entry.load_package()
 lib = pkg._lib.load()
-B, T_x, T_y = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (32, 200, 1000)
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+ragged = "--ragged" in sys.argv
+B, T_x, T_y = (int(a) for a in args[:3]) if len(args) >= 3 else (32, 200, 1000)
 D = 80
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(1)
@@ -22,6 +26,15 @@ for i in range(6):
     sets.append((x_m, x_logs, z))
 xl = torch.full((B,), T_x, dtype=torch.int32, device=dev)
 yl = torch.full((B,), T_y, dtype=torch.int32, device=dev)
+if ragged:
+    tx = torch.randint(T_x // 2, T_x + 1, (B,), generator=g)
+    tx[0] = T_x
+    tx, _ = torch.sort(tx, descending=True)
+    ty = (tx.float() * (T_y / T_x) * (0.8 + 0.4 * torch.rand(B, generator=g))).round().long()
+    ty = torch.minimum(torch.maximum(ty, tx), torch.tensor(T_y)) // 2 * 2
+    ty[0] = T_y
+    xl, yl = tx.to(torch.int32).to(dev), torch.maximum(ty, tx).to(torch.int32).to(dev)
+    print(f"ragged lengths: valid cells {float((xl.float() * yl.float()).sum()) / (B * T_x * T_y):.1%} of the padded batch")
 
 
 def run(i):
