@@ -373,6 +373,13 @@ def run_ours(args):
                         "note": "bounded by the FP32 FMA pipe and the sweep's dependent chain, not by HBM (DESIGN.md 4-5)",
                         "fp32_fma": {"achieved_tflops": flops / (step_ms * 1e-3) / 1e12, "peak_tflops_derived": fp32_peak,
                                      "frac": flops / (step_ms * 1e-3) / 1e12 / fp32_peak, "flops_per_launch": flops},
+                        # what the unfused pipeline must move for the same work: write logp, read logp, write the
+                        # path (12 B/cell) + the inputs.  The compulsory bytes alone cannot reach 50 % of
+                        # the HBM roof: 2x their transfer time leaves room for 1/(2 x 6.1 us) x 2.05 GFLOP = 168 TFLOP/s,
+                        # 2.3x the CUDA-core FP32 peak.
+                        "hbm_equivalent": {"bytes_per_launch": 12 * cells + (in_bytes - 8 * B),
+                                           "achieved": (12 * cells + in_bytes - 8 * B) / (step_ms * 1e-3) / 1e9,
+                                           "frac": (12 * cells + in_bytes - 8 * B) / (step_ms * 1e-3) / 1e9 / peak},
                         "kernel1_alone": k1}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
