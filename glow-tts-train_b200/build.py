@@ -23,12 +23,13 @@ LIB_PATH = PKG_DIR / "libmas_b200.so"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
     # bit-exactness: no fast-math, no flush-to-zero, IEEE div/sqrt (these are the defaults; spelled
     # out so nobody "optimises" them away).  FMA contraction is left on: the DP has no a*b+c
-    # pattern, and the logp contraction uses explicit fmaf().
+    # pattern, and the logp contraction spells its FMAs out (fmaf / fma.rn.f32x2).
     "--ftz=false", "--prec-div=true", "--prec-sqrt=true",
 ]
+OBJ_DIR = PKG_DIR / "build"          # git-ignored object files, one per translation unit
 
 
 def find_nvcc() -> str:
@@ -53,17 +54,35 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}"]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = find_nvcc()
+    OBJ_DIR.mkdir(exist_ok=True)
+    common = [nvcc, *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src: Path):
+        obj = OBJ_DIR / (src.stem + ".o")
+        cmd = common + ["-c", "-o", str(obj), str(src)]
+        return obj, cmd, subprocess.run(cmd, capture_output=True, text=True)
+
+    # the translation units are independent and the template-heavy ones take a minute each: in parallel
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, sources()))
+    objs = []
+    for obj, cmd, proc in results:
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(proc.stdout + proc.stderr)
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed ({proc.returncode}): {' '.join(cmd)}")
+        objs.append(str(obj))
     tmp = LIB_PATH.with_suffix(".so.tmp")
-    cmd += ["-o", str(tmp), *map(str, sources())]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(tmp), *objs]
+    proc = subprocess.run(link, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
         tmp.unlink(missing_ok=True)
-        raise RuntimeError(f"nvcc failed ({proc.returncode}): {' '.join(cmd)}")
+        raise RuntimeError(f"nvcc link failed ({proc.returncode}): {' '.join(link)}")
     tmp.replace(LIB_PATH)
     return LIB_PATH
 
