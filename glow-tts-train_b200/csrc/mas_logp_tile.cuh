@@ -112,7 +112,7 @@ __device__ __forceinline__ void gemm_tile_d(const float *__restrict__ sInv, cons
     const float *pa = sInv + rg * TM, *pb = sMiv + rg * TM;
     const float *pz = sZ + cg * 4;
     const int half = F >> 1;
-#pragma unroll 4
+#pragma unroll 16
     for (int d = 0; d < D; ++d) {
         f32x2 av[TM], bv[TM];
         const float4 b = *reinterpret_cast<const float4 *>(pb);
