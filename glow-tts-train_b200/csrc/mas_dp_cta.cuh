@@ -65,6 +65,34 @@ __host__ __device__ inline Plan make_plan(int R, int W, int S, int K, int T_y, b
 
 __device__ __forceinline__ void spin_fail() { __trap(); }
 
+// The threads that run one utterance's program: a whole CTA (hardware barrier 0), or -- in the
+// single launch, where two utterances share a sweep CTA -- one half of it with a barrier of its own.
+struct Team {
+    int tid, nthr, bar;
+    __device__ __forceinline__ void sync() const {
+        if (bar == 0)
+            __syncthreads();
+        else
+            asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthr) : "memory");
+    }
+    __device__ __forceinline__ int sync_or(int pred) const {
+        if (bar == 0) return __syncthreads_or(pred);
+        uint32_t r;
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q;\n"
+            "setp.ne.u32 q, %1, 0;\n"
+            "bar.red.or.pred p, %2, %3, q;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(r)
+            : "r"(pred), "r"(bar), "r"(nthr)
+            : "memory");
+        return (int)r;
+    }
+};
+__device__ __forceinline__ Team whole_cta() { return Team{(int)threadIdx.x, (int)blockDim.x, 0}; }
+
 __device__ __forceinline__ float fmax_nan(float a, float b) {
     float r;
     asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
@@ -177,11 +205,12 @@ __device__ __forceinline__ void sweep_block(uint32_t tile, const uint32_t (&lane
 // written.  col: [2][tx] floats.  The direction words go where the fast sweep would have put
 // them: word (cb, x) belongs to CTA x / rows, in its shared memory (bits_smem_addr, written over
 // DSMEM) or in the workspace (bits_g, [K][nblk][rows]).
-static __device__ __noinline__ void exact_sweep_cta0(const float *__restrict__ val, int64_t stride_x, float *col, uint32_t bits_smem_addr,
-                                 uint32_t *bits_g, int rows, int nblk, int tx, int ty, float neg) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+static __device__ __noinline__ void exact_sweep_cta0(const Team team, const float *__restrict__ val, int64_t stride_x, float *col,
+                                                     uint32_t bits_smem_addr, uint32_t *bits_g, int rows, int nblk, int tx, int ty,
+                                                     float neg) {
+    const int tid = team.tid, nthr = team.nthr;
     for (int x = tid; x < tx; x += nthr) col[x] = neg;
-    __syncthreads();
+    team.sync();
     int buf = 0;
     for (int y = 0; y < ty; ++y) {
         const float *vin = col + buf * tx;
@@ -204,7 +233,7 @@ static __device__ __noinline__ void exact_sweep_cta0(const float *__restrict__ v
             }
         }
         buf ^= 1;
-        __syncthreads();
+        team.sync();
     }
 }
 
@@ -268,12 +297,12 @@ __device__ __forceinline__ int backtrack_tokens(const uint32_t *bits, int rows, 
 template <int R, bool kDbg, bool kCluster, bool kFused>
 __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams &p, const Plan &plan, unsigned char *smem,
                                        int b, int cta_tag, const int *ready, int ready_target, int chunk_frames = 64,
-                                       int nchunks = 0) {
+                                       int nchunks = 0, const Team team = whole_cta()) {
     float *s_len = reinterpret_cast<float *>(smem + plan.off_misc + 16);
 
     const int K = kCluster ? plan.K : 1;
     const int c = kCluster ? (int)ptx::cluster_ctarank() : 0;    // which slice of the utterance's tokens
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = team.tid, warp = tid >> 5, lane = tid & 31;
     const int W = plan.W, S = plan.S, rows = plan.rows;
     const int T_x = p.T_x, T_y = p.T_y;
     const bool bits_smem = plan.bits_in_smem != 0;
@@ -299,11 +328,11 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         ty_raw = p.t_y[b];
     } else {
         if (tid < 2) s_len[tid] = 0.f;
-        __syncthreads();
+        team.sync();
         float sx = 0.f, sy = 0.f;
         const float *m = p.mask + (int64_t)b * p.mask_stride_b;
-        for (int x = tid; x < T_x; x += blockDim.x) sx += m[(int64_t)x * p.mask_stride_x];
-        for (int y = tid; y < T_y; y += blockDim.x) sy += m[(int64_t)y * p.mask_stride_y];
+        for (int x = tid; x < T_x; x += team.nthr) sx += m[(int64_t)x * p.mask_stride_x];
+        for (int y = tid; y < T_y; y += team.nthr) sy += m[(int64_t)y * p.mask_stride_y];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             sx += __shfl_xor_sync(0xffffffffu, sx, o);
@@ -313,7 +342,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
             atomicAdd(&s_len[0], sx);
             atomicAdd(&s_len[1], sy);
         }
-        __syncthreads();
+        team.sync();
         tx_raw = (int)s_len[0];
         ty_raw = (int)s_len[1];
     }
@@ -348,7 +377,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
     }
     // what "advances" into token 0 after frame 0 (core.pyx:26-27)
     if (c == 0)
-        for (int i = tid; i < kBndBlocks * kBlk; i += blockDim.x) bnd[i] = p.max_neg_val;
+        for (int i = tid; i < kBndBlocks * kBlk; i += team.nthr) bnd[i] = p.max_neg_val;
     // done[1+w] = number of 32-frame blocks warp w has finished.  It starts one short of the warp's
     // first block: the warp still needs the LAST frame of block cb0-1 from its predecessor (the
     // diagonal cell of token x0-1), so that ring slot must not be recycled yet.
@@ -356,7 +385,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
     if (kCluster)
         ptx::cluster_sync();
     else
-        __syncthreads();
+        team.sync();
 
     long long *dbg = (kDbg && p.dbg_cycles && warp < 16) ? p.dbg_cycles + ((size_t)cta_tag * 16 + warp) * 16 : nullptr;
     long long t_wait_prev = 0, t_wait_tma = 0, t_sweep = 0, t_core = 0;
@@ -572,7 +601,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
     }
     if (!bits_smem) __threadfence();
     // ---- were all scores finite?  (cluster-wide) ----
-    const int any_bad = __syncthreads_or(nonfinite);
+    const int any_bad = team.sync_or(nonfinite);
     int redo = any_bad;
     if (kCluster) {
         if (any_bad && tid == 0)
@@ -585,7 +614,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         if (c == 0) {
             float *col = reinterpret_cast<float *>(smem + plan.off_ring);
             const float *val = p.value + (int64_t)b * p.value_stride_b;
-            exact_sweep_cta0(val, p.value_stride_x, col, ptx::smem_u32(bits_s),
+            exact_sweep_cta0(team, val, p.value_stride_x, col, ptx::smem_u32(bits_s),
                              bits_smem ? nullptr : p.ws_bits + (size_t)b * K * plan.nblk * rows, rows, plan.nblk, tx, ty,
                              p.max_neg_val);
             if (!bits_smem) __threadfence();
@@ -593,7 +622,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         if (kCluster)
             ptx::cluster_sync();
         else
-            __syncthreads();
+            team.sync();
     }
 
     // ---- backtrack (core.pyx:32-35) by TOKENS, handed down from CTA to CTA ----
@@ -628,11 +657,11 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         }
     }
     if (kDbg && dbg && tid == 0) dbg[6] = clock64();
-    __syncthreads();
+    team.sync();
 
     // ---- dense path: ones, durations, frame -> token (this CTA's tokens) ----
     float *out = p.path + (int64_t)b * T_x * T_y;
-    for (int xl = tid; xl < rows; xl += blockDim.x) {
+    for (int xl = tid; xl < rows; xl += team.nthr) {
         const int x = xc + xl;
         if (x >= T_x) break;
         int d = 0;
@@ -647,7 +676,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         if (p.durations) p.durations[(int64_t)b * T_x + x] = d;
     }
     if (p.frame_token && c == 0)
-        for (int y = ty + tid; y < T_y; y += blockDim.x) p.frame_token[(int64_t)b * T_y + y] = -1;
+        for (int y = ty + tid; y < T_y; y += team.nthr) p.frame_token[(int64_t)b * T_y + y] = -1;
     if (kDbg && dbg && lane == 0) dbg[7] = clock64();
     if (kDbg && dbg && tid == 0) dbg[13] = ptx::globaltimer_ns();
 }

@@ -37,6 +37,8 @@ struct Geometry {
     TileShape t;
     logp::Deal deal;
     int *ready;        // [B][nchunks] chunk ready counters
+    int teams;         // utterances per sweep CTA: 2 (a half CTA each) when two plans fit one SM, else 1
+    int team_stride;   // bytes of shared memory per team
 };
 
 template <int R, bool kDbg>
@@ -47,10 +49,20 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap, PathParams pp, systol
         // profiling: producers stamp globaltimer per chunk behind the sweep CTAs' [B][16][16] block
         long long *dbg_ns = (kDbg && pp.dbg_cycles) ? pp.dbg_cycles + ((size_t)pp.B * 16 + blockIdx.x) * 16 : nullptr;
         logp::run_deal<true>(lp, reinterpret_cast<float *>(smem), g.t, g.deal, blockIdx.x, g.ready, dbg_ns);
-    } else {
+    } else if (g.teams == 1) {
         const int b = blockIdx.x - g.P;
         systolic::dp_cta<R, kDbg, false, true>(tmap, pp, plan, smem, b, b, g.ready + (size_t)b * g.t.nchunks, g.t.row_tiles,
                                                g.t.F, g.t.nchunks);
+    } else {
+        // two utterances per sweep CTA, half the threads and half the shared memory each, a hardware
+        // barrier of their own: the sweeps then hold B/2 SMs instead of B and the producers get the rest
+        constexpr int kTeam = kThreads / 2;
+        const int team = threadIdx.x / kTeam;
+        const int b = 2 * ((int)blockIdx.x - g.P) + team;
+        if (b >= pp.B) return;
+        systolic::dp_cta<R, kDbg, false, true>(tmap, pp, plan, smem + (size_t)team * g.team_stride, b, b,
+                                               g.ready + (size_t)b * g.t.nchunks, g.t.row_tiles, g.t.F, g.t.nchunks,
+                                               systolic::Team{(int)threadIdx.x - team * kTeam, kTeam, 1 + team});
     }
 }
 
@@ -62,7 +74,7 @@ static int launch_r(const CUtensorMap &tmap, const PathParams &pp, const systoli
     MAS_CUDA_TRY(cudaGetDevice(&dev));
     if (pp.dbg_cycles != nullptr) {
         MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        mas_fused_kernel<R, true><<<g.P + pp.B, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
+        mas_fused_kernel<R, true><<<g.P + (pp.B + g.teams - 1) / g.teams, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
         MAS_CUDA_TRY(cudaGetLastError());
         return MAS_OK;
     }
@@ -77,7 +89,7 @@ static int launch_r(const CUtensorMap &tmap, const PathParams &pp, const systoli
         cudaFuncGetAttributes(&fa, mas_fused_kernel<R, false>);
         fprintf(stderr, "[mas_b200] fused kernel: %d CTAs/SM resident, %d regs, %zu B static smem\n", nb, fa.numRegs, fa.sharedSizeBytes);
     }
-    mas_fused_kernel<R, false><<<g.P + pp.B, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
+    mas_fused_kernel<R, false><<<g.P + (pp.B + g.teams - 1) / g.teams, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
     MAS_CUDA_TRY(cudaGetLastError());
     return MAS_OK;
 }
@@ -122,29 +134,56 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
     const int max_smem = max_smem_cached[dev] - 2048;
     const int num_sms = num_sms_cached[dev];
 
-    // a sweep CTA per utterance on its own SM, the other SMs produce; past a third of the SMs the
-    // producers become the long pole and two full-width launches are faster
     Geometry g{};
     g.t = make_tile_shape(T_x, T_y);
     const int BT = B * g.t.row_tiles;
-    g.P = num_sms - B;
-    if (3 * B > num_sms || BT > g.P) MAS_FUSED_NO("too many utterances for one wave");
-    g.deal = logp::make_deal(g.P, BT, g.t.nchunks);
     const int gemm_smem = logp::cta_smem_floats(D, g.t) * 4;
     if (gemm_smem > max_smem) MAS_FUSED_NO("shared memory (producers)");
 
-    // sweep CTAs: K = 1, deepest ring that fits
+    // sweep CTAs (K = 1): one utterance per CTA with the deepest ring that fits.
+    // Experiment hook MAS_B200_FUSED_TWO_TEAMS: two utterances per sweep CTA (a half CTA -- 8 warps --
+    // and half the shared memory each), so that the sweeps hold B/2 SMs and the producers get 16
+    // more.  Measured at C2: the producers then finish at 58 us instead of 69, but the sweeps -- two
+    // per scheduler, ring only two boxes deep -- take 55 us instead of 42 and become the critical
+    // path: 110 us per step against 94.  Off by default.
+    static const bool two_teams = getenv("MAS_B200_FUSED_TWO_TEAMS") != nullptr;
     systolic::Plan plan{};
     bool ok = false;
+    g.teams = 1;
+    if (two_teams && B > 1) {
+        const int groups = ceil_div(T_x, systolic::kBlk);
+        for (int r : {R, 2, 3, 5, 4, 6, 8}) {
+            const int w = ceil_div(groups, r);
+            if (w + 1 > kThreads / 64) continue;                      // 8 warps per team
+            for (int S = 4; S >= 2 && !ok; --S) {
+                systolic::Plan pl = systolic::make_plan(r, w, S, 1, T_y, true, 8192);
+                const int stride = (int)align_up((size_t)pl.total, 1024);
+                if (2 * stride <= max_smem) {
+                    plan = pl;
+                    g.teams = 2;
+                    g.team_stride = stride;
+                    ok = true;
+                }
+            }
+            if (ok) break;
+        }
+    }
     for (int bits_smem = 1; bits_smem >= 0 && !ok; --bits_smem)
         for (int S = 4; S >= 2 && !ok; --S) {
             plan = systolic::make_plan(R, W, S, 1, T_y, bits_smem != 0, 8192);
             ok = plan.total <= max_smem;
         }
     if (!ok) MAS_FUSED_NO("shared memory (sweep)");
-    int smem_bytes = gemm_smem > plan.total ? gemm_smem : plan.total;
+    const int sweep_smem = g.teams == 2 ? 2 * g.team_stride : plan.total;
+    int smem_bytes = gemm_smem > sweep_smem ? gemm_smem : sweep_smem;
     const int solo = (max_smem_cached[dev] + 1024) / 2;                 // more than half an SM: one CTA per SM
     if (smem_bytes < solo) smem_bytes = solo;
+
+    // the SMs the sweeps do not hold produce; with fewer than two producers per token tile they
+    // would be the long pole and two full-width launches are faster
+    g.P = num_sms - ceil_div(B, g.teams);
+    if (g.P < 2 * BT) MAS_FUSED_NO("too many utterances for one wave");
+    g.deal = logp::make_deal(g.P, BT, g.t.nchunks);
 
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     float *scores = reinterpret_cast<float *>(ws);
@@ -182,8 +221,9 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) MAS_FUSED_NO("tensor map encode failed");
     if (debug)
-        fprintf(stderr, "[mas_b200] single launch: %d producers (%d per tile + %d spares, cover %d of %d chunks of %d frames, tiles of %d tokens) + %d sweep CTAs, %d B smem, R=%d W=%d S=%d\n",
-                g.P, g.deal.d, g.deal.spares, g.deal.cover, g.t.nchunks, g.t.F, g.t.tile_rows, B, smem_bytes, plan.R, plan.W, plan.S);
+        fprintf(stderr, "[mas_b200] single launch: %d producers (%d per tile + %d spares, cover %d of %d chunks of %d frames, tiles of %d tokens) + %d sweep CTAs of %d utterance(s), %d B smem, R=%d W=%d S=%d\n",
+                g.P, g.deal.d, g.deal.spares, g.deal.cover, g.t.nchunks, g.t.F, g.t.tile_rows, ceil_div(B, g.teams), g.teams, smem_bytes,
+                plan.R, plan.W, plan.S);
 
     switch (plan.R) {
         case 1: return launch_r<1>(tmap, pp, plan, lp, g, smem_bytes, stream);
