@@ -1,0 +1,45 @@
+"""Random shapes, lengths and channel counts through the fused entry for a few minutes, every result
+checked against the oracle (path and durations bit-exact on our scores, scores within 1e-5 of fp64):
+  python profiles/fuzz_fused.py [seconds]        (B200, round 1: 1 863 shapes in 150 s, 0 failures)"""
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import __graft_entry__ as entry  # noqa: E402
+pkg = entry.load_package()
+oracle = entry.load_oracle()
+from conftest import ragged_lengths  # noqa: E402
+from test_fused_gpu import synth_prior, to_dev  # noqa: E402
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 150.0
+rng = np.random.default_rng(20261018)
+t0 = time.time(); n = 0; bad = 0
+while time.time() - t0 < budget:
+    B = int(rng.integers(1, 50)); T_x = int(rng.integers(1, 320)); T_y = int(rng.integers(T_x, 1300))
+    if rng.random() < 0.7: T_y = (T_y + 3) // 4 * 4
+    D = 80 if rng.random() < 0.8 else int(rng.integers(1, 100))
+    mean_only = bool(rng.random() < 0.4)
+    t_x, t_y = ragged_lengths(rng, B, T_x, T_y)
+    if rng.random() < 0.3: t_x[:] = T_x; t_y[:] = T_y
+    x_m, x_logs, z = synth_prior(rng, B, D, T_x, T_y, t_x, t_y, mean_only)
+    args = (to_dev(x_m), to_dev(x_logs), to_dev(z), torch.from_numpy(t_x), torch.from_numpy(t_y))
+    poison = torch.full((pkg._lib.load().mas_b200_fused_workspace_bytes(B, D, T_x, T_y) // 4 + 64,), float('nan'), device='cuda:0'); del poison
+    path, dur, tok = pkg.fused_maximum_path(*args, want_frame_token=True)
+    logp = pkg.log_likelihood_matrix(*args[:3])
+    k1 = pkg.maximum_path_from_lengths(logp, to_dev(t_x), to_dev(t_y))
+    ok = torch.equal(k1, path)
+    want = oracle.maximum_path(logp.cpu().numpy(), t_x, t_y)
+    ok = ok and np.array_equal(path.cpu().numpy().astype(np.int32), want) and np.array_equal(dur.cpu().numpy(), want.sum(-1))
+    ref64 = oracle.logp_f64(x_m, x_logs, z)
+    rel = np.max(np.abs(logp.cpu().numpy() - ref64) / np.maximum(np.abs(ref64), 1.0))
+    ok = ok and rel < 1e-5
+    n += 1
+    if not ok:
+        bad += 1; print('FAIL', B, D, T_x, T_y, mean_only, rel, flush=True)
+print(f'{n} shapes, {bad} failures')

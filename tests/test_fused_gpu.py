@@ -173,3 +173,32 @@ def test_single_launch_ignores_garbage_in_the_score_scratch(pkg, oracle):
     logp = pkg.log_likelihood_matrix(*args[:3]).cpu().numpy()
     assert np.array_equal(path.cpu().numpy().astype(np.int32), oracle.maximum_path(logp, t_x, t_y))
     assert np.array_equal(dur.cpu().numpy(), path.cpu().numpy().sum(-1).astype(np.int32))
+
+
+def test_fused_random_shapes(pkg, oracle):
+    """A seeded slice of profiles/fuzz_fused.py: random batch sizes, lengths, channel counts and
+    (un)aligned frame counts through every path the fused entry can take."""
+    rng = np.random.default_rng(20261018)
+    lib = pkg._lib.load()
+    for _ in range(24):
+        B, T_x = int(rng.integers(1, 50)), int(rng.integers(1, 320))
+        T_y = int(rng.integers(T_x, 1300))
+        if rng.random() < 0.7:
+            T_y = (T_y + 3) // 4 * 4
+        D = 80 if rng.random() < 0.8 else int(rng.integers(1, 100))
+        mean_only = bool(rng.random() < 0.4)
+        t_x, t_y = ragged_lengths(rng, B, T_x, T_y)
+        if rng.random() < 0.3:
+            t_x[:], t_y[:] = T_x, T_y
+        x_m, x_logs, z = synth_prior(rng, B, D, T_x, T_y, t_x, t_y, mean_only)
+        args = (to_dev(x_m), to_dev(x_logs), to_dev(z), torch.from_numpy(t_x), torch.from_numpy(t_y))
+        poison = torch.full((lib.mas_b200_fused_workspace_bytes(B, D, T_x, T_y) // 4 + 64,), float("nan"), device=DEV)
+        del poison
+        path, dur = pkg.fused_maximum_path(*args)
+        logp = pkg.log_likelihood_matrix(*args[:3])
+        want = oracle.maximum_path(logp.cpu().numpy(), t_x, t_y)
+        assert np.array_equal(path.cpu().numpy().astype(np.int32), want), (B, D, T_x, T_y, mean_only)
+        assert np.array_equal(dur.cpu().numpy(), want.sum(-1)), (B, D, T_x, T_y, mean_only)
+        ref64 = oracle.logp_f64(x_m, x_logs, z)
+        rel = np.max(np.abs(logp.cpu().numpy() - ref64) / np.maximum(np.abs(ref64), 1.0))
+        assert rel < LOGP_RTOL, (B, D, T_x, T_y, mean_only, rel)
