@@ -111,7 +111,8 @@ int mas_b200_maximum_path_f32(const float *value, int64_t value_stride_b, int64_
  * the unfused pipeline stage):
  *   logp[b,x,y] = sum_d(-0.5*log(2pi) - logs[b,d,x]) + sum_d exp(-2 logs[b,d,x]) * (-0.5 z[b,d,y]^2)
  *               + sum_d (m[b,d,x] exp(-2 logs[b,d,x])) * z[b,d,y] + sum_d -0.5 m[b,d,x]^2 exp(-2 logs[b,d,x])
- * summed as ((l1+l2)+l3)+l4 in fp32 (FFMA contraction over channels, ascending d).
+ * in fp32: (l1 + c) + l4 with c = one accumulator over channels ascending (the l2 and l3 terms
+ * interleaved); ((l1+l2)+l3)+l4 when x_logs == NULL.  Within 1e-5 relative of the fp64 formula.
  *   x_m, x_logs [B][D][T_x] fp32 device contiguous; x_logs NULL == zeros (mean_only, config.py:52)
  *   z           [B][D][T_y] fp32 device contiguous
  *   logp        [B][T_x][T_y] fp32 device contiguous
@@ -121,8 +122,10 @@ int mas_b200_logp_f32(const float *x_m, const float *x_logs, const float *z, flo
 
 /*
  * Kernel (2): log-likelihood + alignment search in one launch: producer CTAs contract the scores in
- * 64-frame chunks, sweep CTAs consume them as they appear (ready flags), through an L2-resident
- * scratch in the workspace.  Replaces models.py:362-382 (+ :393 through `durations`).
+ * chunks of 64-128 frames, sweep CTAs consume them as they appear (ready flags), through an
+ * L2-resident scratch in the workspace.  Batches too large for one wave (more than ~#SMs/3
+ * utterances) and shapes the single launch does not support run as two launches inside the same
+ * call, same results.  Replaces models.py:362-382 (+ :393 through `durations`).
  *   x_len, y_len int32 [B] device: valid tokens / frames (what the prefix masks encode).
  * Other arguments as above.  logp tiles are accurate to 1e-5 relative against the fp64 formula;
  * the path equals kernel (1) run on mas_b200_logp_f32's output bit for bit.
