@@ -18,6 +18,7 @@ from .alignment import (  # noqa: F401
     aligned_mle_loss,
     expand_prior,
     fused_maximum_path,
+    generate_path,
     log_durations,
     log_likelihood_matrix,
     maximum_path_from_lengths,
@@ -31,6 +32,7 @@ __all__ = [
     "log_likelihood_matrix",
     "expand_prior",
     "log_durations",
+    "generate_path",
     "aligned_mle_loss",
     "monotonic_align",
     "alignment",

@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "mas_b200_expand_prior_f32",
     "mas_b200_expand_prior_backward_f32",
     "mas_b200_log_durations_f32",
+    "mas_b200_generate_path_f32",
     "mas_b200_mle_loss_workspace_bytes",
     "mas_b200_mle_loss_f32",
     "mas_b200_mle_loss_backward_f32",
@@ -91,6 +92,8 @@ def load() -> ctypes.CDLL:
     lib.mas_b200_expand_prior_backward_f32.argtypes = [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]
     lib.mas_b200_log_durations_f32.restype = _i32
     lib.mas_b200_log_durations_f32.argtypes = [_vp, _vp, _vp, _i32, _i32, _vp]
+    lib.mas_b200_generate_path_f32.restype = _i32
+    lib.mas_b200_generate_path_f32.argtypes = [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _vp]
     lib.mas_b200_mle_loss_workspace_bytes.restype = ctypes.c_size_t
     lib.mas_b200_mle_loss_workspace_bytes.argtypes = [_i32, _i32]
     lib.mas_b200_mle_loss_f32.restype = _i32

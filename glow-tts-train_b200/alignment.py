@@ -271,3 +271,24 @@ def aligned_mle_loss(z, x_m, x_logs, logdet, frame_token, durations, y_lengths):
     y_len = y_lengths.to(device=z.device, dtype=torch.int32).contiguous()
     return _AlignedMleLoss.apply(z.contiguous(), x_m.contiguous(), None if x_logs is None else x_logs.contiguous(), logdet,
                                  frame_token.contiguous(), durations.contiguous(), y_len)
+
+
+def generate_path(duration, mask):
+    """``generate_path(duration, mask)`` of the reference (utils.py:99-115, the inference branch at
+    models.py:340): ``duration`` [B, T_x] (ceil-ed frame counts, any float/int dtype), ``mask``
+    [B, T_x, T_y] (a strided view is fine) -> dense path [B, T_x, T_y] in ``mask``'s dtype."""
+    lib = _lib.load()
+    _require_cuda(duration, "duration")
+    _require_cuda(mask, "mask")
+    if duration.dim() != 2 or mask.dim() != 3 or tuple(mask.shape[:2]) != tuple(duration.shape):
+        raise ValueError("duration must be [B, T_x] and mask [B, T_x, T_y]")
+    B, T_x, T_y = mask.shape
+    m32 = mask if mask.dtype == torch.float32 else mask.float()
+    d32 = duration.float().contiguous()
+    out = torch.empty((B, T_x, T_y), dtype=torch.float32, device=mask.device)
+    if out.numel():
+        with torch.cuda.device(mask.device):
+            rc = lib.mas_b200_generate_path_f32(d32.data_ptr(), m32.data_ptr(), m32.stride(0), m32.stride(1), m32.stride(2),
+                                                out.data_ptr(), B, T_x, T_y, _stream(mask.device))
+        _lib.check(rc, "mas_b200_generate_path_f32")
+    return out if mask.dtype == torch.float32 else out.to(mask.dtype)

@@ -187,6 +187,16 @@ int mas_b200_log_durations_f32(const int32_t *durations, const int32_t *x_len, f
     return launch_logw(durations, x_len, logw, B, T_x, static_cast<cudaStream_t>(stream));
 }
 
+int mas_b200_generate_path_f32(const float *duration, const float *mask, int64_t mask_stride_b, int64_t mask_stride_x,
+                               int64_t mask_stride_y, float *path, int B, int T_x, int T_y, mas_stream_t stream) {
+    if (B < 0 || T_x < 0 || T_y < 0) return MAS_ERR_INVALID_ARGUMENT;
+    if (!shape_ok(B, T_x, T_y)) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (B == 0 || T_x == 0 || T_y == 0) return MAS_OK;
+    if (!duration || !mask || !path) return MAS_ERR_INVALID_ARGUMENT;
+    return launch_generate_path(duration, mask, mask_stride_b, mask_stride_x, mask_stride_y, path, B, T_x, T_y,
+                                static_cast<cudaStream_t>(stream));
+}
+
 size_t mas_b200_mle_loss_workspace_bytes(int B, int T_y) {
     if (B <= 0 || T_y <= 0) return 0;
     return mle_loss_workspace_bytes(B, T_y);

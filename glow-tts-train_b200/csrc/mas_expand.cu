@@ -86,3 +86,62 @@ int launch_logw(const int32_t *durations, const int32_t *x_len, float *logw, int
 }
 
 }  // namespace mas
+
+// ---------------------------------------------------------------------------------------------
+// SURVEY.md 8(f) rank 4, the inference-side analogue: durations -> dense path
+// (glow_tts_train/utils.py:99-115 `generate_path`, called at models.py:340):
+//   cum[x] = duration[b,0] + ... + duration[b,x]       (fp32, ascending; exact for the integer-valued
+//                                                        ceil(w) the model passes, < 2^24)
+//   path[b,x,y] = ((y < cum[x]) - (y < cum[x-1])) * mask[b,x,y]          (cum[-1] = 0)
+// One CTA per (utterance, 32 tokens): prefix sums in shared memory, then every warp writes token
+// rows with 16-byte stores.  HBM-bound: 4 B/cell written (+ 4 B/cell of mask read, as the reference does).
+// ---------------------------------------------------------------------------------------------
+namespace mas {
+namespace expand {
+
+constexpr int kGenRows = 32;
+
+__global__ void __launch_bounds__(256) generate_path_kernel(const float *__restrict__ duration, const float *__restrict__ mask,
+                                                            int64_t ms_b, int64_t ms_x, int64_t ms_y, float *__restrict__ path,
+                                                            int T_x, int T_y) {
+    extern __shared__ float s_cum[];                      // [T_x + 1], s_cum[0] = 0
+    const int b = blockIdx.y, x0 = blockIdx.x * kGenRows;
+    const float *du = duration + (int64_t)b * T_x;
+    if (threadIdx.x == 0) {
+        float run = 0.f;
+        s_cum[0] = 0.f;
+        const int upto = min(T_x, x0 + kGenRows);
+        for (int x = 0; x < upto; ++x) {                  // torch.cumsum order; only the prefix this CTA needs
+            run += du[x];
+            s_cum[x + 1] = run;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int xr = warp; xr < kGenRows; xr += 8) {
+        const int x = x0 + xr;
+        if (x >= T_x) break;
+        const float lo = s_cum[x], hi = s_cum[x + 1];
+        float *row = path + ((int64_t)b * T_x + x) * T_y;
+        const float *mrow = mask + (int64_t)b * ms_b + (int64_t)x * ms_x;
+        for (int y = lane; y < T_y; y += 32) {
+            const float fy = (float)y;                    // sequence_mask compares arange in the length's dtype (utils.py:52-56)
+            const float v = (float)(fy < hi) - (float)(fy < lo);
+            row[y] = v * mrow[(int64_t)y * ms_y];
+        }
+    }
+}
+
+}  // namespace expand
+
+int launch_generate_path(const float *duration, const float *mask, int64_t ms_b, int64_t ms_x, int64_t ms_y, float *path, int B,
+                         int T_x, int T_y, cudaStream_t stream) {
+    if (B == 0 || T_x == 0 || T_y == 0) return MAS_OK;
+    dim3 grid(ceil_div(T_x, expand::kGenRows), B);
+    expand::generate_path_kernel<<<grid, 256, (size_t)(T_x + 1) * sizeof(float), stream>>>(duration, mask, ms_b, ms_x, ms_y, path,
+                                                                                             T_x, T_y);
+    MAS_CUDA_TRY(cudaGetLastError());
+    return MAS_OK;
+}
+
+}  // namespace mas

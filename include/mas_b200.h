@@ -152,6 +152,17 @@ int mas_b200_expand_prior_backward_f32(const float *dz, const int32_t *durations
 int mas_b200_log_durations_f32(const int32_t *durations, const int32_t *x_len, float *logw, int B, int T_x, mas_stream_t stream);
 
 /*
+ * SURVEY.md 8f rank 4, the inference-side analogue of the path: `generate_path(duration, mask)`
+ * (glow_tts_train/utils.py:99-115, called at models.py:340): cum = cumsum(duration) per utterance,
+ *   path[b,x,y] = ((y < cum[b,x]) - (y < cum[b,x-1])) * mask[b,x,y]
+ * duration fp32 [B][T_x] contiguous (the model passes ceil(w): integer-valued, for which the fp32
+ * running sum is exact), mask fp32 [B,T_x,T_y] with ELEMENT strides (the reference passes the view
+ * attn_mask.squeeze(1)), path fp32 [B][T_x][T_y] contiguous, fully written.
+ */
+int mas_b200_generate_path_f32(const float *duration, const float *mask, int64_t mask_stride_b, int64_t mask_stride_x,
+                               int64_t mask_stride_y, float *path, int B, int T_x, int T_y, mas_stream_t stream);
+
+/*
  * the maximum-likelihood loss of the aligned prior, `mle_loss(z, z_m, z_logs,
  * logdet, z_mask)` (glow_tts_train/utils.py:14-23, called at train.py:124), from the TOKEN-level prior
  * and the frame->token map -- z_m / z_logs (models.py:383-392) are never materialised:

@@ -100,3 +100,39 @@ def test_aligned_mle_loss_matches_reference(pkg, shape, mean_only):
     # deterministic: a second evaluation gives the same bits
     loss2 = pkg.aligned_mle_loss(z, x_m, x_logs, logdet, tok, dur, ty_d)
     assert torch.equal(loss, loss2)
+
+
+def reference_generate_path(duration, mask):
+    """utils.py:99-115 verbatim (sequence_mask :52-56, convert_pad_shape :41-44 inlined)."""
+    import torch.nn.functional as F
+    b, t_x, t_y = mask.shape
+    cum_duration = torch.cumsum(duration, 1)
+    cum_duration_flat = cum_duration.view(b * t_x)
+    x = torch.arange(t_y, dtype=cum_duration_flat.dtype, device=duration.device)
+    path = (x.unsqueeze(0) < cum_duration_flat.unsqueeze(1)).to(mask.dtype)
+    path = path.view(b, t_x, t_y)
+    path = path - F.pad(path, [0, 0, 1, 0, 0, 0])[:, :-1]
+    path = path * mask
+    return path
+
+
+@pytest.mark.parametrize("shape", [(3, 37, 150), (4, 200, 1000), (1, 1, 1), (2, 64, 50)])
+def test_generate_path_matches_reference(pkg, shape):
+    """the inference-side durations -> path expansion (models.py:340)."""
+    B, T_x, T_y = shape
+    rng = np.random.default_rng(B * 31 + T_x)
+    t_x, _ = ragged_lengths(rng, B, T_x, max(T_x, T_y))
+    x_mask = (torch.arange(T_x, device=DEV)[None] < torch.from_numpy(t_x).to(DEV)[:, None]).float()
+    # ceil-ed durations as models.py:330-333 makes them; the frame budget comes from their sum (:334)
+    w_ceil = torch.ceil(torch.rand(B, T_x, device=DEV) * 2 * T_y / T_x) * x_mask
+    y_len = torch.clamp_min(w_ceil.sum(1), 1).long()
+    y_mask = (torch.arange(T_y, device=DEV)[None] < y_len[:, None]).float()
+    attn_mask = (x_mask.unsqueeze(-1) * y_mask.unsqueeze(1)).unsqueeze(1)          # [b,1,t_x,t_y], models.py:334-337
+    want = reference_generate_path(w_ceil, attn_mask.squeeze(1))
+    got = pkg.generate_path(w_ceil, attn_mask.squeeze(1))
+    assert got.dtype == want.dtype and got.shape == want.shape
+    assert torch.equal(got, want)
+    # a strided mask view and integer durations give the same path
+    wide = torch.zeros(B, T_x, T_y + 5, device=DEV)
+    wide[:, :, :T_y] = attn_mask.squeeze(1)
+    assert torch.equal(pkg.generate_path(w_ceil.long(), wide[:, :, :T_y]), want)
