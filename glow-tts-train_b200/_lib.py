@@ -23,6 +23,8 @@ EXPORTED_SYMBOLS = (
     "mas_b200_debug_set_cycle_buffer",
     "mas_b200_debug_force_cluster",
     "mas_b200_debug_force_unfused",
+    "mas_b200_debug_tile_shape",
+    "mas_b200_debug_deal",
     "mas_b200_workspace_bytes",
     "mas_b200_fused_workspace_bytes",
     "mas_b200_maximum_path_f32",
@@ -62,6 +64,10 @@ def load() -> ctypes.CDLL:
     lib.mas_b200_debug_set_cycle_buffer.argtypes = [_vp]
     lib.mas_b200_debug_force_cluster.restype = None
     lib.mas_b200_debug_force_cluster.argtypes = [_i32]
+    lib.mas_b200_debug_tile_shape.restype = _i32
+    lib.mas_b200_debug_tile_shape.argtypes = [_i32, _i32, _vp]
+    lib.mas_b200_debug_deal.restype = _i32
+    lib.mas_b200_debug_deal.argtypes = [_i32, _i32, _i32, _vp, _vp]
     lib.mas_b200_debug_force_unfused.restype = None
     lib.mas_b200_debug_force_unfused.argtypes = [_i32]
     lib.mas_b200_workspace_bytes.restype = _sz

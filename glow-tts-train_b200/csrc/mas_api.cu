@@ -197,6 +197,14 @@ int mas_b200_generate_path_f32(const float *duration, const float *mask, int64_t
                                 static_cast<cudaStream_t>(stream));
 }
 
+int mas_b200_debug_deal(int P, int BT, int nchunks, int32_t *owner, int32_t *order) { return debug_deal(P, BT, nchunks, owner, order); }
+
+int mas_b200_debug_tile_shape(int T_x, int T_y, int32_t *out6) {
+    if (T_x <= 0 || T_y <= 0 || !out6) return MAS_ERR_INVALID_ARGUMENT;
+    debug_tile_shape(T_x, T_y, out6);
+    return MAS_OK;
+}
+
 size_t mas_b200_mle_loss_workspace_bytes(int B, int T_y) {
     if (B <= 0 || T_y <= 0) return 0;
     return mle_loss_workspace_bytes(B, T_y);

@@ -46,6 +46,8 @@ int launch_expand_scatter(const float *dz, const int32_t *durations, float *dx, 
 int launch_logw(const int32_t *durations, const int32_t *x_len, float *logw, int B, int T_x, cudaStream_t stream);
 int launch_generate_path(const float *duration, const float *mask, int64_t ms_b, int64_t ms_x, int64_t ms_y, float *path, int B,
                          int T_x, int T_y, cudaStream_t stream);
+int debug_deal(int P, int BT, int nchunks, int32_t *owner, int32_t *order);   // host only (mas_logp.cu)
+void debug_tile_shape(int T_x, int T_y, int32_t *out6);                        // host only
 size_t mle_loss_workspace_bytes(int B, int T_y);
 int launch_mle_loss(const float *z, const float *x_m, const float *x_logs, const int32_t *frame_token, const float *logdet,
                     const int32_t *y_len, float *out2, void *workspace, int B, int D, int T_x, int T_y, cudaStream_t stream);

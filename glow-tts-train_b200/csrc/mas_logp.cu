@@ -139,4 +139,35 @@ int launch_logp(const LogpParams &p, cudaStream_t stream) {
     return MAS_OK;
 }
 
+// Host-side enumeration of the deal (no device needed): which CTA takes chunk c of row r, and as
+// the how-manieth chunk of its share.  Returns the number of (row, chunk) units assigned more than
+// once (0 for a correct deal); units nobody takes keep owner -1.
+int debug_deal(int P, int BT, int nchunks, int32_t *owner, int32_t *order) {
+    using namespace logp;
+    if (P <= 0 || BT <= 0 || nchunks <= 0 || !owner || !order) return -1;
+    for (int64_t i = 0; i < (int64_t)BT * nchunks; ++i) owner[i] = order[i] = -1;
+    const Deal q = make_deal(P, BT, nchunks);
+    int doubles = 0;
+    for (int pidx = 0; pidx < P; ++pidx) {
+        int pos = 0;
+        DealPiece o;
+        for (int it = 0; deal_piece(q, pidx, it, o); ++it)
+            for (int k = 0; k < o.count; ++k) {
+                int c = o.first + k * o.stride;
+                if (c >= o.skip_from) c += q.nchunks - q.cover;
+                if (o.r < 0 || o.r >= BT || c < 0 || c >= nchunks) return -2;
+                int32_t &w = owner[(int64_t)o.r * nchunks + c];
+                if (w >= 0) ++doubles;
+                w = pidx;
+                order[(int64_t)o.r * nchunks + c] = pos++;
+            }
+    }
+    return doubles;
+}
+
+void debug_tile_shape(int T_x, int T_y, int32_t *out6) {
+    const TileShape t = make_tile_shape(T_x, T_y);
+    out6[0] = t.row_tiles, out6[1] = t.tile_rows, out6[2] = t.RG, out6[3] = t.CG, out6[4] = t.F, out6[5] = t.nchunks;
+}
+
 }  // namespace mas

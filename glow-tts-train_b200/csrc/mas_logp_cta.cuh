@@ -272,37 +272,51 @@ inline Deal make_deal(int P, int BT, int nchunks) {
     return q;
 }
 
+// The `it`-th piece of CTA `pidx`'s share: row `r`, chunks first, first + stride, ... (`count` of them,
+// numbers from `skip_from` up shifted by the spares' range, see logp_cta).  False when the CTA is done.
+// Host and device: the kernels walk it, the debug entry of the C ABI enumerates it for the CPU tests.
+struct DealPiece {
+    int r, first, stride, count, skip_from;
+};
+__host__ __device__ inline bool deal_piece(const Deal &q, int pidx, int it, DealPiece &o) {
+    const int base = q.passes * q.P, dedicated = q.d * q.rem, left = (q.nchunks - q.cover) * q.rem;
+    o.stride = 1;
+    o.count = 1;
+    o.skip_from = 0x7fffffff;
+    if (it < q.passes) {                                // a whole row
+        o.r = it * q.P + pidx;
+        o.first = 0;
+        o.count = q.nchunks;
+        return true;
+    }
+    if (q.rem == 0) return false;
+    if (pidx < dedicated) {                             // dedicated CTA j of a remaining row
+        if (it > q.passes) return false;
+        const int rr = pidx / q.d, j = pidx - rr * q.d;
+        o.r = base + rr;
+        o.first = j;
+        o.stride = q.d;
+        o.count = (q.cover - j + q.d - 1) / q.d;
+        o.skip_from = q.spare_first;                    // (== cover or beyond when the spares take the end)
+        return o.count > 0;
+    }
+    const int u = (pidx - dedicated) + (it - q.passes) * q.spares;   // spare: one left-over chunk at a time
+    if (q.spares <= 0 || u >= left) return false;
+    const int l = u / q.rem;
+    o.r = base + (u - l * q.rem);
+    o.first = q.spare_first + l;
+    return true;
+}
+
 // Runs CTA `pidx`'s share.  ready: [B][nchunks] counters (kSignal only).  One call site of logp_cta:
 // the program is a few thousand instructions and instruction fetch is not free.
 template <bool kSignal>
 __device__ __forceinline__ void run_deal(const LogpParams &p, float *sm, const TileShape &t, const Deal &q, int pidx, int *ready,
                                          long long *dbg_ns = nullptr) {
-    const int base = q.passes * q.P, dedicated = q.d * q.rem, per_row = q.nchunks - q.cover, left = per_row * q.rem;
-    for (int it = 0;; ++it) {
-        int r, first, stride = 1, count = 1, skip_from = 0x7fffffff;
-        if (it < q.passes) {                            // a whole row
-            r = it * q.P + pidx;
-            first = 0;
-            count = q.nchunks;
-        } else if (q.rem == 0) {
-            break;
-        } else if (pidx < dedicated) {                  // dedicated CTA j of a remaining row
-            if (it > q.passes) break;
-            const int rr = pidx / q.d, j = pidx - rr * q.d;
-            r = base + rr;
-            first = j;
-            stride = q.d;
-            count = (q.cover - j + q.d - 1) / q.d;
-            skip_from = q.spare_first;                  // (== cover or beyond when the spares take the end)
-        } else {                                        // spare: one left-over chunk at a time
-            const int u = (pidx - dedicated) + (it - q.passes) * q.spares;
-            if (u >= left) break;
-            const int l = u / q.rem;
-            r = base + (u - l * q.rem);
-            first = q.spare_first + l;
-        }
-        const int b = r / t.row_tiles, rt = r - b * t.row_tiles;
-        logp_cta<kSignal>(p, sm, t, b, rt * t.tile_rows, first, stride, count, skip_from, per_row,
+    DealPiece o;
+    for (int it = 0; deal_piece(q, pidx, it, o); ++it) {
+        const int b = o.r / t.row_tiles, rt = o.r - b * t.row_tiles;
+        logp_cta<kSignal>(p, sm, t, b, rt * t.tile_rows, o.first, o.stride, o.count, o.skip_from, q.nchunks - q.cover,
                           kSignal ? ready + (size_t)b * q.nchunks : nullptr, dbg_ns);
     }
 }

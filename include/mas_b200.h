@@ -63,6 +63,13 @@ void mas_b200_debug_force_cluster(int ctas_per_utterance);
 /* Testing hook: non-zero makes mas_b200_fused_maximum_path_f32 run its two programs as two launches
  * (the path it takes anyway for shapes the single launch does not support). */
 void mas_b200_debug_force_unfused(int on);
+/* Testing hooks, HOST only (no device needed): how the contraction's work is laid out.
+ *   debug_tile_shape: out6 = {row_tiles, tile_rows, row groups, column groups, frames per chunk, chunks}
+ *   debug_deal: the deal of (row, chunk) units to P persistent CTAs (rows = utterances x row_tiles):
+ *     owner[r * nchunks + c] = the CTA that contracts chunk c of row r (-1: nobody), order[...] = its
+ *     position in that CTA's sequence; returns how many units were dealt twice (0), < 0 on bad arguments. */
+int mas_b200_debug_tile_shape(int T_x, int T_y, int32_t *out6);
+int mas_b200_debug_deal(int P, int BT, int nchunks, int32_t *owner, int32_t *order);
 /* MAS_OK iff the current CUDA device can run the kernels (compute capability 10.x). */
 int mas_b200_device_ok(void);
 

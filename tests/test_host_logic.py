@@ -119,3 +119,60 @@ def test_sharded_equals_single_gloo(tmp_path, oracle, pkg):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     ok = np.load(tmp_path / "ok.npy")
     assert ok.all()
+
+
+def _deal(lib, P, BT, nchunks):
+    owner = np.empty(BT * nchunks, np.int32)
+    order = np.empty(BT * nchunks, np.int32)
+    rc = lib.mas_b200_debug_deal(P, BT, nchunks, owner.ctypes.data, order.ctypes.data)
+    return rc, owner.reshape(BT, nchunks), order.reshape(BT, nchunks)
+
+
+def test_contraction_units_are_dealt_exactly_once(pkg):
+    """Host logic of the contraction kernels (csrc/mas_logp_cta.cuh `Deal`): every (row, chunk) unit goes
+    to exactly one persistent CTA, whatever the numbers of CTAs, rows and chunks."""
+    lib = pkg._lib.load()
+    rng = np.random.default_rng(5)
+    combos = [(148, 32, 13), (116, 32, 13), (148, 160, 2), (148, 148, 7), (148, 149, 7), (1, 5, 3), (7, 1, 40),
+              (132, 32, 13), (100, 48, 13), (148, 1, 13), (3, 3, 1)]
+    combos += [tuple(int(v) for v in (rng.integers(1, 200), rng.integers(1, 400), rng.integers(1, 40))) for _ in range(300)]
+    for P, BT, n in combos:
+        rc, owner, order = _deal(lib, P, BT, n)
+        assert rc == 0, (P, BT, n, rc)
+        assert owner.min() >= 0 and owner.max() < P, (P, BT, n)
+        # a CTA walks the chunks of a row in ascending order: early frames first
+        for r in range(BT):
+            for cta in np.unique(owner[r]):
+                mine = np.flatnonzero(owner[r] == cta)
+                assert np.all(np.diff(order[r, mine]) > 0), (P, BT, n, r, cta)
+
+
+def test_contraction_deal_at_the_benchmark_shapes(pkg):
+    """C2 (32 utterances x 13 chunks): the materialising kernel needs 3 rounds on 148 SMs, the single
+    launch 4 on the 116 SMs the sweeps leave, where the spare CTAs have the time to take chunk 9, just
+    before the dedicated CTAs' last round; with 3 rounds they take the last chunk."""
+    lib = pkg._lib.load()
+    for P, rounds in ((148, 3), (116, 4)):
+        rc, owner, order = _deal(lib, P, 32, 13)
+        assert rc == 0
+        per_cta = np.bincount(owner.ravel(), minlength=P)
+        dedicated = per_cta[: (P // 32) * 32]
+        assert dedicated.max() == rounds and dedicated.min() >= rounds - 1
+        spares = per_cta[(P // 32) * 32:]
+        assert spares.sum() == 32 and spares.max() <= 2
+        spare_chunks = {int(c) for r in range(32) for c in np.flatnonzero(owner[r] >= (P // 32) * 32)}
+        assert spare_chunks == ({9} if P == 116 else {12})
+
+
+def test_contraction_tile_shapes(pkg):
+    """csrc/mas_logp_tile.cuh `make_tile_shape`: at most 512 threads of 4 x 8 cells, whole utterance covered."""
+    lib = pkg._lib.load()
+    out = np.empty(6, np.int32)
+    for T_x, T_y in [(200, 1000), (1, 1), (7, 8), (256, 64), (257, 264), (400, 2000), (1024, 8192), (2048, 65536), (50, 122)]:
+        assert lib.mas_b200_debug_tile_shape(T_x, T_y, out.ctypes.data) == 0
+        row_tiles, tile_rows, RG, CG, F, nchunks = (int(v) for v in out)
+        assert RG * CG <= 512 and 8 <= CG <= 16 and F == 8 * CG and tile_rows == 4 * RG and tile_rows <= 256
+        assert row_tiles * tile_rows >= T_x and (row_tiles - 1) * tile_rows < T_x
+        assert nchunks * F >= T_y and (nchunks - 1) * F < T_y
+    lib.mas_b200_debug_tile_shape(200, 1000, out.ctypes.data)
+    assert tuple(out) == (1, 200, 50, 10, 80, 13)
