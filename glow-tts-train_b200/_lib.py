@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = (
     "mas_b200_debug_force_cluster",
     "mas_b200_debug_force_unfused",
     "mas_b200_debug_tile_shape",
+    "mas_b200_debug_path_plan",
     "mas_b200_debug_deal",
     "mas_b200_workspace_bytes",
     "mas_b200_fused_workspace_bytes",
@@ -66,6 +67,8 @@ def load() -> ctypes.CDLL:
     lib.mas_b200_debug_force_cluster.argtypes = [_i32]
     lib.mas_b200_debug_tile_shape.restype = _i32
     lib.mas_b200_debug_tile_shape.argtypes = [_i32, _i32, _vp]
+    lib.mas_b200_debug_path_plan.restype = _i32
+    lib.mas_b200_debug_path_plan.argtypes = [_i32, _i32, _i32, _i32, _i32, _vp]
     lib.mas_b200_debug_deal.restype = _i32
     lib.mas_b200_debug_deal.argtypes = [_i32, _i32, _i32, _vp, _vp]
     lib.mas_b200_debug_force_unfused.restype = None

@@ -38,7 +38,8 @@ int launch_path_simple(PathParams p, void *workspace, size_t workspace_bytes, cu
 size_t path_systolic_workspace_bytes(int B, int T_x, int T_y);
 // MAS_ERR_UNSUPPORTED_SHAPE = "not for the TMA path": the caller falls back to launch_path_simple.
 int launch_path_systolic(PathParams p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
-void path_systolic_force_cluster(int k);   // testing hook: CTAs per utterance (0 = heuristic)
+void path_systolic_force_cluster(int k);
+bool debug_path_plan(int B, int T_x, int T_y, int max_smem, int num_sms, int32_t *out8);   // host only   // testing hook: CTAs per utterance (0 = heuristic)
 
 // path consumers (mas_expand.cu)
 int launch_expand_gather(const float *x, const int32_t *frame_token, float *z, int B, int D, int T_x, int T_y, cudaStream_t stream);

@@ -126,6 +126,16 @@ static int launch_r(const CUtensorMap &tmap, const PathParams &p, const Plan &pl
 
 void path_systolic_force_cluster(int k) { systolic::g_force_cluster = k; }
 
+// Host-only: the plan the launcher would pick on a device with `max_smem` bytes of opt-in shared
+// memory per CTA and `num_sms` SMs.  out8 = {R, W, S, K, rows, nblk, bits_in_smem, total bytes}.
+bool debug_path_plan(int B, int T_x, int T_y, int max_smem, int num_sms, int32_t *out8) {
+    systolic::Plan pl{};
+    if (!systolic::choose_plan(B, T_x, T_y, max_smem, num_sms, pl)) return false;
+    out8[0] = pl.R, out8[1] = pl.W, out8[2] = pl.S, out8[3] = pl.K, out8[4] = pl.rows, out8[5] = pl.nblk;
+    out8[6] = pl.bits_in_smem, out8[7] = pl.total;
+    return true;
+}
+
 size_t path_systolic_workspace_bytes(int B, int T_x, int T_y) {
     // upper bound over every plan the heuristic may pick: tokens rounded up per CTA, K <= 8
     size_t worst = 0;

@@ -69,6 +69,11 @@ void mas_b200_debug_force_unfused(int on);
  *     owner[r * nchunks + c] = the CTA that contracts chunk c of row r (-1: nobody), order[...] = its
  *     position in that CTA's sequence; returns how many units were dealt twice (0), < 0 on bad arguments. */
 int mas_b200_debug_tile_shape(int T_x, int T_y, int32_t *out6);
+/*   debug_path_plan: kernel (1)'s geometry on a device with `max_smem` bytes of opt-in shared memory per
+ *     CTA and `num_sms` SMs: out8 = {tokens per lane, sweep warps, TMA ring depth, CTAs per utterance,
+ *     tokens per CTA, 32-frame blocks, direction bits in shared memory?, shared memory bytes};
+ *     MAS_ERR_UNSUPPORTED_SHAPE when the TMA path cannot take the shape. */
+int mas_b200_debug_path_plan(int B, int T_x, int T_y, int max_smem, int num_sms, int32_t *out8);
 int mas_b200_debug_deal(int P, int BT, int nchunks, int32_t *owner, int32_t *order);
 /* MAS_OK iff the current CUDA device can run the kernels (compute capability 10.x). */
 int mas_b200_device_ok(void);

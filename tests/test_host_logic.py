@@ -176,3 +176,30 @@ def test_contraction_tile_shapes(pkg):
         assert nchunks * F >= T_y and (nchunks - 1) * F < T_y
     lib.mas_b200_debug_tile_shape(200, 1000, out.ctypes.data)
     assert tuple(out) == (1, 200, 50, 10, 80, 13)
+
+
+def test_sweep_plans(pkg):
+    """Host logic of kernel (1) (`choose_shape` / `choose_plan`): tokens covered, shared memory within
+    the device's limit, one CTA per utterance unless capacity needs a cluster."""
+    lib = pkg._lib.load()
+    out = np.empty(8, np.int32)
+    max_smem, num_sms = 232448 - 2048, 148                      # B200: opt-in shared memory per CTA, SMs
+    want = {
+        (32, 200, 1000): (3, 3, 1, 1),                          # R, W, K, bits in shared memory
+        (256, 400, 2000): (3, 5, 1, 0),                         # 129 KB of direction bits: in the workspace
+        (8, 1024, 8192): (2, 2, 8, 1),                          # long form: 8 CTAs per utterance hold the bits
+        (32, 1024, 8192): (3, 3, 4, 0),
+        (2, 5, 36): (1, 1, 1, 1),
+    }
+    rng = np.random.default_rng(9)
+    shapes = list(want) + [(int(rng.integers(1, 300)), int(rng.integers(1, 2049)), 0) for _ in range(200)]
+    for B, T_x, T_y in shapes:
+        if T_y == 0:
+            T_y = int(rng.integers(max(T_x, 32), 65537)) // 4 * 4
+        rc = lib.mas_b200_debug_path_plan(B, T_x, T_y, max_smem, num_sms, out.ctypes.data)
+        assert rc == 0, (B, T_x, T_y, rc)
+        R, W, S, K, rows, nblk, bits_smem, total = (int(v) for v in out)
+        assert rows == 32 * R * W and rows * K >= T_x and nblk == -(-T_y // 32)
+        assert 2 <= S <= 4 and K in (1, 2, 4, 8) and W <= 15 and total <= max_smem
+        if (B, T_x, T_y) in want:
+            assert (R, W, K, bits_smem) == want[(B, T_x, T_y)], (B, T_x, T_y, out.tolist())
