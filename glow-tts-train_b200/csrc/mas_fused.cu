@@ -39,6 +39,7 @@ struct Geometry {
     int *ready;        // [B][nchunks] chunk ready counters
     int teams;         // utterances per sweep CTA: 2 (a half CTA each) when two plans fit one SM, else 1
     int team_stride;   // bytes of shared memory per team
+    int head;          // chunks 0 .. head-1 of an utterance are produced by its own sweep CTA first
 };
 
 template <int R, bool kDbg>
@@ -48,9 +49,17 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap, PathParams pp, systol
     if ((int)blockIdx.x < g.P) {
         // profiling: producers stamp globaltimer per chunk behind the sweep CTAs' [B][16][16] block
         long long *dbg_ns = (kDbg && pp.dbg_cycles) ? pp.dbg_cycles + ((size_t)pp.B * 16 + blockIdx.x) * 16 : nullptr;
-        logp::run_deal<true>(lp, reinterpret_cast<float *>(smem), g.t, g.deal, blockIdx.x, g.ready, dbg_ns);
+        logp::run_deal<true>(lp, reinterpret_cast<float *>(smem), g.t, g.deal, blockIdx.x, g.ready, g.head, dbg_ns);
     } else if (g.teams == 1) {
         const int b = blockIdx.x - g.P;
+        // experiment hook (launch_fused): head chunks of the own utterance first
+        if (g.head > 0) {
+            for (int rt = 0; rt < g.t.row_tiles; ++rt)
+                logp::logp_cta<true>(lp, reinterpret_cast<float *>(smem), g.t, b, rt * g.t.tile_rows, 0, 1, g.head, 0x7fffffff, 0, 0,
+                                     g.ready + (size_t)b * g.t.nchunks, nullptr);
+            __syncthreads();                            // the shared memory changes hands
+            ptx::fence_proxy_async();                   // generic-proxy writes before the TMA boxes land there
+        }
         systolic::dp_cta<R, kDbg, false, true>(tmap, pp, plan, smem, b, b, g.ready + (size_t)b * g.t.nchunks, g.t.row_tiles,
                                                g.t.F, g.t.nchunks);
     } else {
@@ -183,7 +192,21 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
     // would be the long pole and two full-width launches are faster
     g.P = num_sms - ceil_div(B, g.teams);
     if (g.P < 2 * BT) MAS_FUSED_NO("too many utterances for one wave");
-    g.deal = logp::make_deal(g.P, BT, g.t.nchunks);
+    // Experiment hook MAS_B200_FUSED_HEAD=n: the sweep CTA of an utterance contracts its first n
+    // chunks itself (its SM idles until the first scores exist) and the producers' deal covers the
+    // rest.  Measured at C2 (graph of 10 steps): n = 0 / 1 / 2 / 3 -> 99 / 109 / 120 / 137 us per step.
+    // A head chunk costs the sweep CTA a full unit although most of its cells are below the diagonal
+    // (17-20 us: the sweep starts at 27 / 44 us instead of 24), the sweep itself needs 55-60 us after
+    // its start, and 12 or 11 chunks over three producers are still four rounds.  Off by default.
+    g.head = 0;
+    if (g.teams == 1) {
+        static const char *head_env = getenv("MAS_B200_FUSED_HEAD");
+        g.head = head_env ? atoi(head_env) : 0;
+        const int cap = g.t.nchunks / 4;                // the sweep still has most of the utterance to wait for
+        if (g.head > cap) g.head = cap;
+        if (g.head < 0) g.head = 0;
+    }
+    g.deal = logp::make_deal(g.P, BT, g.t.nchunks - g.head);
 
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     float *scores = reinterpret_cast<float *>(ws);
@@ -221,8 +244,8 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) MAS_FUSED_NO("tensor map encode failed");
     if (debug)
-        fprintf(stderr, "[mas_b200] single launch: %d producers (%d per tile + %d spares, cover %d of %d chunks of %d frames, tiles of %d tokens) + %d sweep CTAs of %d utterance(s), %d B smem, R=%d W=%d S=%d\n",
-                g.P, g.deal.d, g.deal.spares, g.deal.cover, g.t.nchunks, g.t.F, g.t.tile_rows, ceil_div(B, g.teams), g.teams, smem_bytes,
+        fprintf(stderr, "[mas_b200] single launch: %d producers (%d per tile + %d spares, cover %d of %d chunks of %d frames after %d head chunks, tiles of %d tokens) + %d sweep CTAs of %d utterance(s), %d B smem, R=%d W=%d S=%d\n",
+                g.P, g.deal.d, g.deal.spares, g.deal.cover, g.deal.nchunks, g.t.F, g.head, g.t.tile_rows, ceil_div(B, g.teams), g.teams, smem_bytes,
                 plan.R, plan.W, plan.S);
 
     switch (plan.R) {

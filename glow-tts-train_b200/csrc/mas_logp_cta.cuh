@@ -22,11 +22,13 @@ __host__ __device__ inline int cta_smem_floats(int D, const TileShape &t) {
 }
 
 // chunks chunk_first, chunk_first + chunk_stride, ... (chunk_count of them) of token tile x0 of
-// utterance b; indices from skip_from up are shifted by skip_by (the chunks the spare CTAs take)
+// utterance b; indices from skip_from up are shifted by skip_by (the chunks the spare CTAs take);
+// the whole numbering starts at chunk `chunk_base` of the utterance (single launch: the chunks
+// before it are produced by the utterance's own sweep CTA, mas_fused.cu)
 template <bool kSignal>
 __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, const TileShape &t, int b, int x0, int chunk_first,
-                                         int chunk_stride, int chunk_count, int skip_from, int skip_by, int *ready,
-                                         long long *dbg_ns = nullptr) {
+                                         int chunk_stride, int chunk_count, int skip_from, int skip_by, int chunk_base,
+                                         int *ready, long long *dbg_ns = nullptr) {
     if (chunk_count <= 0) return;
     const int D = p.D, T_x = p.T_x, T_y = p.T_y;
     const int tile_rows = t.tile_rows, F = t.F, CG = t.CG;
@@ -74,10 +76,10 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, const T
     int seq = chunk_first;
     auto next_chunk = [&](int) {
         seq += chunk_stride;
-        return seq >= skip_from ? seq + skip_by : seq;
+        return (seq >= skip_from ? seq + skip_by : seq) + chunk_base;
     };
     __syncthreads();                                    // a previous tile of this CTA is done with the shared memory
-    int ch = seq >= skip_from ? seq + skip_by : seq;
+    int ch = (seq >= skip_from ? seq + skip_by : seq) + chunk_base;
     if (dbg_ns && tid == 0) dbg_ns[0] = ptx::globaltimer_ns();
     stage_frames_async(ch, 0);                          // in flight while the token side is prepared
     // token side: thread (x, h) stages token x0+x for one contiguous share of the channels (coalesced
@@ -308,16 +310,17 @@ __host__ __device__ inline bool deal_piece(const Deal &q, int pidx, int it, Deal
     return true;
 }
 
-// Runs CTA `pidx`'s share.  ready: [B][nchunks] counters (kSignal only).  One call site of logp_cta:
-// the program is a few thousand instructions and instruction fetch is not free.
+// Runs CTA `pidx`'s share.  ready: [B][t.nchunks] counters (kSignal only).  The deal covers chunks
+// chunk_base .. t.nchunks - 1 of every row (q.nchunks == t.nchunks - chunk_base).  One call site of
+// logp_cta per kind of CTA: the program is a few thousand instructions and instruction fetch is not free.
 template <bool kSignal>
 __device__ __forceinline__ void run_deal(const LogpParams &p, float *sm, const TileShape &t, const Deal &q, int pidx, int *ready,
-                                         long long *dbg_ns = nullptr) {
+                                         int chunk_base = 0, long long *dbg_ns = nullptr) {
     DealPiece o;
     for (int it = 0; deal_piece(q, pidx, it, o); ++it) {
         const int b = o.r / t.row_tiles, rt = o.r - b * t.row_tiles;
-        logp_cta<kSignal>(p, sm, t, b, rt * t.tile_rows, o.first, o.stride, o.count, o.skip_from, q.nchunks - q.cover,
-                          kSignal ? ready + (size_t)b * q.nchunks : nullptr, dbg_ns);
+        logp_cta<kSignal>(p, sm, t, b, rt * t.tile_rows, o.first, o.stride, o.count, o.skip_from, q.nchunks - q.cover, chunk_base,
+                          kSignal ? ready + (size_t)b * t.nchunks : nullptr, dbg_ns);
     }
 }
 
