@@ -302,7 +302,12 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
 
     const int K = kCluster ? plan.K : 1;
     const int c = kCluster ? (int)ptx::cluster_ctarank() : 0;    // which slice of the utterance's tokens
-    const int tid = team.tid, warp = tid >> 5, lane = tid & 31;
+    const int tid = team.tid, lane = tid & 31;
+    // broadcast from lane 0 so that the compiler KNOWS the warp index is warp-uniform: the role
+    // branches and block loops below are then uniform control flow and the per-frame SHFL.UP of the
+    // sweep is a plain shuffle (with `tid >> 5` every one of them was wrapped in WARPSYNC.COLLECTIVE /
+    // ENDCOLLECTIVE plus three register moves, five extra issue slots per frame of a lone warp)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int W = plan.W, S = plan.S, rows = plan.rows;
     const int T_x = p.T_x, T_y = p.T_y;
     const bool bits_smem = plan.bits_in_smem != 0;
