@@ -16,8 +16,9 @@ namespace systolic {
 
 
 constexpr int kBlk = 32;            // frames per box / per direction word
+constexpr int kPubBlocks = 2;      // blocks between two publications of a sweep warp's progress
 constexpr int kMaxDpWarps = 15;     // + 1 filler warp = 512 threads
-constexpr int kBndBlocks = 4;       // depth of the warp-to-warp boundary ring, in 32-frame blocks
+constexpr int kBndBlocks = 8;       // depth of the warp-to-warp boundary ring, in 32-frame blocks
 constexpr int kDoneAll = 0x3fffffff;
 constexpr uint32_t kSpinLimit = 1u << 27;   // watchdog: a wedged wait traps instead of hanging the GPU
 
@@ -447,17 +448,35 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                 lane_c[i] = (uint32_t)(row * kBlk * 4) | (uint32_t)((row & 7) << 4);
             }
 
-            for (int cb = cb0; cb <= cbend; ++cb) {
+            // Progress is exchanged with the neighbour warps once per kPub blocks: the polls, the release
+            // store (a MEMBAR) and the mirrors cost a lone warp a few hundred cycles, as much as a third
+            // of a block's sweep.  The price is one more block of skew per warp, and the boundary ring
+            // must be deep enough for producer and consumer to overlap (with 4 blocks and steps of 2 they
+            // alternated: 41 -> 58 us at 200 x 1000).  No deadlock while
+            // 2 kPubBlocks <= kBndBlocks: a producer stuck before the step ending at block h_p has published
+            // h_p - kPubBlocks + 1 and needs its consumer past h_p - kBndBlocks; the consumer stuck before
+            // its step ending at h_c needs the producer past h_c -- both at once would need
+            // h_c >= h_p - kPubBlocks + 1 and h_c <= h_p - kBndBlocks + kPubBlocks - 1.
+            static_assert(2 * kPubBlocks <= kBndBlocks, "boundary ring too shallow for the publication step");
+            // Measured (profiles/r1_sweep_k.txt): with the neighbour in another CTA (polls and mirrors
+            // over DSMEM) two blocks per publication take 13-21 % off the 1024 x 8192 cluster shapes;
+            // inside one CTA the extra skew costs more than the saved polls (41.1 -> 42.8 us at 200 x 1000),
+            // so K = 1 publishes every block.
+            constexpr int kPub = kCluster ? kPubBlocks : 1;
+            for (int cbs = cb0; cbs <= cbend; cbs += kPub) {
+                const int cb_hi = min(cbs + kPub - 1, cbend);
                 uint32_t spins = 0;
                 const long long t0 = kDbg ? clock64() : 0;
-                while (seen_prev <= cb) {                       // previous warp has published block cb
+                while (seen_prev <= cb_hi) {                    // previous warp has published blocks .. cb_hi
                     seen_prev = prev_remote ? ptx::ld_acquire_cluster_shared_a(done_prev_a) : ptx::ld_acquire_shared_a(done_prev_a);
                     if (++spins > kSpinLimit) spin_fail();
                 }
-                while (seen_next + kBndBlocks <= cb) {          // next warp has consumed block cb - ring depth
+                while (seen_next + kBndBlocks <= cb_hi) {       // next warp has consumed block cb_hi - ring depth
                     seen_next = next_remote ? ptx::ld_acquire_cluster_shared_a(done_next_a) : ptx::ld_acquire_shared_a(done_next_a);
                     if (++spins > kSpinLimit) spin_fail();
                 }
+                if (kDbg) t_wait_prev += clock64() - t0;
+              for (int cb = cbs; cb <= cb_hi; ++cb) {
                 const long long t2 = kDbg ? clock64() : 0;
                 const uint32_t slot8 = (uint32_t)slot * 8u;
                 while (!ptx::mbar_try_wait_a(full_a + slot8, parity))
@@ -499,13 +518,6 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                     for (int i = 0; i < R; ++i) bits_gp[i] = acc[i];
                     bits_gp += rows;
                 }
-                // lane 31 wrote the boundary scores, so lane 31 publishes the progress (program order +
-                // release); remote mirrors first, the local counter last
-                if (kCluster) {
-                    ptx::st_release_cluster_if(lane31 && mirror_prev != 0u, mirror_prev, cb + 1);
-                    ptx::st_release_cluster_if(lane31 && mirror_next != 0u, mirror_next, cb + 1);
-                }
-                ptx::st_release_shared_if_a(lane31, done_self_a, cb + 1);
                 __syncwarp();                                  // every lane has read the box: hand the slot back
                 ptx::mbar_arrive_if_a(lane0, empty_a + slot8);  // the loader warp refills it
                 if (++slot == S) {
@@ -513,10 +525,17 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                     parity ^= 1u;
                 }
                 if (kDbg) {
-                    t_wait_prev += t2 - t0;
                     t_wait_tma += t3 - t2;
                     t_sweep += clock64() - t3;
                 }
+              }
+                // lane 31 wrote the boundary scores, so lane 31 publishes the progress (program order +
+                // release); remote mirrors first, the local counter last
+                if (kCluster) {
+                    ptx::st_release_cluster_if(lane31 && mirror_prev != 0u, mirror_prev, cb_hi + 1);
+                    ptx::st_release_cluster_if(lane31 && mirror_next != 0u, mirror_next, cb_hi + 1);
+                }
+                ptx::st_release_shared_if_a(lane31, done_self_a, cb_hi + 1);
             }
             if (kCluster) {
                 ptx::st_release_cluster_if(lane31 && mirror_prev != 0u, mirror_prev, kDoneAll);
