@@ -16,9 +16,9 @@ namespace systolic {
 
 
 constexpr int kBlk = 32;            // frames per box / per direction word
-constexpr int kPubBlocks = 2;      // blocks between two publications of a sweep warp's progress
+constexpr int kPubBlocks = 4;      // blocks between two publications of a sweep warp's progress
 constexpr int kMaxDpWarps = 15;     // + 1 filler warp = 512 threads
-constexpr int kBndBlocks = 8;       // depth of the warp-to-warp boundary ring, in 32-frame blocks
+constexpr int kBndBlocks = 16;      // depth of the warp-to-warp boundary ring, in 32-frame blocks
 constexpr int kDoneAll = 0x3fffffff;
 constexpr uint32_t kSpinLimit = 1u << 27;   // watchdog: a wedged wait traps instead of hanging the GPU
 
@@ -459,7 +459,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
             // h_c >= h_p - kPubBlocks + 1 and h_c <= h_p - kBndBlocks + kPubBlocks - 1.
             static_assert(2 * kPubBlocks <= kBndBlocks, "boundary ring too shallow for the publication step");
             // Measured (profiles/r1_sweep_k.txt): with the neighbour in another CTA (polls and mirrors
-            // over DSMEM) two blocks per publication take 13-21 % off the 1024 x 8192 cluster shapes;
+            // over DSMEM) four blocks per publication take 22-27 % off the 1024 x 8192 cluster shapes;
             // inside one CTA the extra skew costs more than the saved polls (41.1 -> 42.8 us at 200 x 1000),
             // so K = 1 publishes every block.
             constexpr int kPub = kCluster ? kPubBlocks : 1;
