@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "mas_b200_logp_f32",
     "mas_b200_fused_maximum_path_f32",
     "mas_b200_maximum_path_host_i32",
+    "mas_b200_shutdown",
     "mas_b200_expand_prior_f32",
     "mas_b200_expand_prior_backward_f32",
     "mas_b200_log_durations_f32",
@@ -111,6 +112,8 @@ def load() -> ctypes.CDLL:
     lib.mas_b200_mle_loss_backward_f32.argtypes = [_vp] * 9 + [_i32] * 4 + [_vp]
     lib.mas_b200_maximum_path_host_i32.restype = _i32
     lib.mas_b200_maximum_path_host_i32.argtypes = [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32]
+    lib.mas_b200_shutdown.restype = None
+    lib.mas_b200_shutdown.argtypes = []
     _lib = lib
     return lib
 

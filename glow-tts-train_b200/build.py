@@ -3,8 +3,11 @@
     python glow-tts-train_b200/build.py [--force] [--verbose]
 
 nvcc cross-compiles without a GPU; the resulting .so sits next to this file so that it travels to
-the GPU box with the repository snapshot.  cudart is linked statically (nvcc default), so the
-library has no dependency on torch or on a particular libcudart.so at run time.
+the GPU box with the repository snapshot.  The CUDA runtime is linked as a SHARED library
+(`-cudart shared`; libcudart.so.12, found through the process -- torch has loaded its copy by the
+time the binding loads this library -- or through the rpath /usr/local/cuda/lib64): the static
+runtime would embed every runtime entry-point name in the product, including batch-copy calls the
+library never makes.
 """
 from __future__ import annotations
 
@@ -59,10 +62,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = find_nvcc()
     OBJ_DIR.mkdir(exist_ok=True)
     common = [nvcc, *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}"] + (["-Xptxas", "-v"] if verbose else [])
+    headers = list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h")) + [Path(__file__)]
+    newest_header = max(h.stat().st_mtime for h in headers)
 
     def compile_one(src: Path):
         obj = OBJ_DIR / (src.stem + ".o")
         cmd = common + ["-c", "-o", str(obj), str(src)]
+        # a translation unit is rebuilt when it or any header changed (the template-heavy ones take minutes)
+        if not force and not verbose and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, newest_header):
+            return obj, cmd, subprocess.CompletedProcess(cmd, 0, "", "")
         return obj, cmd, subprocess.run(cmd, capture_output=True, text=True)
 
     # the translation units are independent and the template-heavy ones take a minute each: in parallel
@@ -76,7 +84,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed ({proc.returncode}): {' '.join(cmd)}")
         objs.append(str(obj))
     tmp = LIB_PATH.with_suffix(".so.tmp")
-    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(tmp), *objs]
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared",
+            "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-o", str(tmp), *objs]
     proc = subprocess.run(link, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

@@ -1,6 +1,7 @@
 // mas_api.cu -- the extern "C" surface declared in include/mas_b200.h: argument validation,
 // workspace carving and kernel dispatch.  No torch, no exceptions, no host synchronisation
 // (except mas_b200_maximum_path_host_i32, which is synchronous by contract).
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -9,17 +10,36 @@
 
 namespace mas {
 thread_local int g_last_cuda_error = 0;
-long long *g_dbg_cycles = nullptr;
+std::atomic<long long *> g_dbg_cycles{nullptr};
 }
-static int g_force_unfused = 0;   // testing hook: run the two kernels back to back
+static std::atomic<int> g_force_unfused{0};   // testing hook: run the two kernels back to back
 
 using namespace mas;
+
+namespace mas {
+int get_device_info(int dev, DeviceInfo &out) {
+    static std::mutex mu;
+    static DeviceInfo cache[64];
+    static bool have[64] = {false};
+    if (dev < 0 || dev >= 64) return MAS_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!have[dev]) {
+        DeviceInfo d{};
+        MAS_CUDA_TRY(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        MAS_CUDA_TRY(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
+        cache[dev] = d;
+        have[dev] = true;
+    }
+    out = cache[dev];
+    return MAS_OK;
+}
+}  // namespace mas
 
 namespace {
 
 size_t path_workspace_bytes(int B, int T_x, int T_y) {
     const size_t a = path_simple_workspace_bytes(B, T_x, T_y), b = path_systolic_workspace_bytes(B, T_x, T_y);
-    return a > b ? a : b;
+    return (a > b ? a : b) + mask_flag_bytes(B);       // + the per-utterance "mask is not all-ones" flags (mas_mask.cu)
 }
 
 struct FusedWorkspace {
@@ -58,11 +78,11 @@ const char *mas_b200_status_string(int status) {
 
 int mas_b200_last_cuda_error(void) { return g_last_cuda_error; }
 
-void mas_b200_debug_set_cycle_buffer(void *device_buffer) { g_dbg_cycles = static_cast<long long *>(device_buffer); }
+void mas_b200_debug_set_cycle_buffer(void *device_buffer) { g_dbg_cycles.store(static_cast<long long *>(device_buffer)); }
 
 void mas_b200_debug_force_cluster(int ctas_per_utterance) { path_systolic_force_cluster(ctas_per_utterance); }
 
-void mas_b200_debug_force_unfused(int on) { g_force_unfused = on; }
+void mas_b200_debug_force_unfused(int on) { g_force_unfused.store(on); }
 
 int mas_b200_device_ok(void) {
     int dev = 0, major = 0;
@@ -115,7 +135,20 @@ int mas_b200_maximum_path_f32(const float *value, int64_t value_stride_b, int64_
     p.T_x = T_x;
     p.T_y = T_y;
     p.max_neg_val = max_neg_val;
-    p.dbg_cycles = g_dbg_cycles;
+    p.dbg_cycles = g_dbg_cycles.load();
+    if (t_x == nullptr) {
+        // lengths AND scores come through the mask (__init__.py:11,18-19): prove on the device that
+        // value * mask == value on the valid rectangle; utterances where it is not are flagged and
+        // computed from value * mask literally
+        const size_t fb = mask_flag_bytes(B);
+        if (workspace == nullptr || workspace_bytes < fb) return MAS_ERR_WORKSPACE_TOO_SMALL;
+        int *flags = reinterpret_cast<int *>(static_cast<unsigned char *>(workspace) + workspace_bytes - fb);
+        flags = reinterpret_cast<int *>(reinterpret_cast<uintptr_t>(flags) & ~(uintptr_t)3);
+        int rcm = launch_mask_check(p, flags, static_cast<cudaStream_t>(stream));
+        if (rcm != MAS_OK) return rcm;
+        p.exact_flag = flags;
+        workspace_bytes -= fb;
+    }
     // the TMA-staged systolic kernel when shape/alignment allow, else the generic kernel
     int rc = launch_path_systolic(p, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if (rc != MAS_ERR_UNSUPPORTED_SHAPE) return rc;
@@ -146,7 +179,7 @@ int mas_b200_fused_maximum_path_f32(const float *x_m, const float *x_logs, const
     FusedWorkspace w = fused_ws(B, T_x, T_y);
     if (workspace == nullptr || workspace_bytes < mas_b200_fused_workspace_bytes(B, D, T_x, T_y)) return MAS_ERR_WORKSPACE_TOO_SMALL;
     // One launch: producer CTAs (FFMA contraction) and sweep CTAs run concurrently (mas_fused.cu).
-    if (!g_force_unfused) {
+    if (!g_force_unfused.load()) {
         LogpParams lp{x_m, x_logs, z, nullptr, B, D, T_x, T_y};
         const int rc1 = launch_fused(lp, x_len, y_len, path, durations, frame_token, workspace, workspace_bytes, max_neg_val,
                                      static_cast<cudaStream_t>(stream));
@@ -298,13 +331,36 @@ int mas_b200_maximum_path_host_i32(int32_t *paths, const float *values, const in
                                        max_neg_val, s.stream);
         if (rc != MAS_OK) break;
         // int32 result written over the (no longer needed) staged scores
-        path_f32_to_i32_kernel<<<148 * 4, 256, 0, s.stream>>>(static_cast<float *>(s.d_path), static_cast<int32_t *>(s.d_value), cells);
+        int num_sms = 0;
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || num_sms <= 0) num_sms = 128;
+        path_f32_to_i32_kernel<<<num_sms * 4, 256, 0, s.stream>>>(static_cast<float *>(s.d_path), static_cast<int32_t *>(s.d_value), cells);
         if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e); break; }
         if ((e = cudaMemcpyAsync(paths, s.d_value, cells * 4, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) { rc = cuda_fail(e); break; }
         if ((e = cudaStreamSynchronize(s.stream)) != cudaSuccess) { rc = cuda_fail(e); break; }
     } while (false);
     cudaSetDevice(prev_dev);
     return rc;
+}
+
+// Frees the staging buffers and the stream the host entry keeps per device.  The library holds no
+// other resources; safe to call at any time no host entry is running, and more than once.
+void mas_b200_shutdown(void) {
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    int prev_dev = 0;
+    if (cudaGetDevice(&prev_dev) != cudaSuccess) return;
+    for (int d = 0; d < 64; ++d) {
+        HostStage &s = g_stage[d];
+        if (!s.d_value && !s.d_path && !s.d_len && !s.d_ws && !s.stream) continue;
+        if (cudaSetDevice(d) != cudaSuccess) continue;
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_value);
+        cudaFree(s.d_path);
+        cudaFree(s.d_len);
+        cudaFree(s.d_ws);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        s = HostStage{};
+    }
+    cudaSetDevice(prev_dev);
 }
 
 }  // extern "C"

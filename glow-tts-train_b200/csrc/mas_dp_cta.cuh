@@ -206,9 +206,12 @@ __device__ __forceinline__ void sweep_block(uint32_t tile, const uint32_t (&lane
 // written.  col: [2][tx] floats.  The direction words go where the fast sweep would have put
 // them: word (cb, x) belongs to CTA x / rows, in its shared memory (bits_smem_addr, written over
 // DSMEM) or in the workspace (bits_g, [K][nblk][rows]).
+// msk: null, or the utterance's mask (element strides ms_x, ms_y): the scores are then value * mask
+// as monotonic_align/__init__.py:11 forms them (utterances flagged by mas_mask.cu).
 static __device__ __noinline__ void exact_sweep_cta0(const Team team, const float *__restrict__ val, int64_t stride_x, float *col,
                                                      uint32_t bits_smem_addr, uint32_t *bits_g, int rows, int nblk, int tx, int ty,
-                                                     float neg) {
+                                                     float neg, const float *__restrict__ msk = nullptr, int64_t ms_x = 0,
+                                                     int64_t ms_y = 0) {
     const int tid = team.tid, nthr = team.nthr;
     for (int x = tid; x < tx; x += nthr) col[x] = neg;
     team.sync();
@@ -219,7 +222,8 @@ static __device__ __noinline__ void exact_sweep_cta0(const Team team, const floa
         for (int x = tid; x < tx; x += nthr) {
             const float stay = vin[x];                                      // == -1e9 while x > y-1, core.pyx:19-20
             const float adv = (x == 0) ? ((y == 0) ? 0.f : neg) : vin[x - 1];   // core.pyx:23-29
-            const float l = (x > y) ? 0.f : __ldg(val + (int64_t)x * stride_x + y);
+            float l = (x > y) ? 0.f : __ldg(val + (int64_t)x * stride_x + y);
+            if (msk != nullptr && x <= y) l *= __ldg(msk + (int64_t)x * ms_x + (int64_t)y * ms_y);
             const bool take = adv > stay;
             vout[x] = (take ? adv : stay) + l;
             const uint32_t bit = ((take || (x == y && x > 0)) ? 1u : 0u) << (y & 31);
@@ -625,7 +629,8 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
     }
     if (!bits_smem) __threadfence();
     // ---- were all scores finite?  (cluster-wide) ----
-    const int any_bad = team.sync_or(nonfinite);
+    const bool masked = !kFused && p.exact_flag != nullptr && p.exact_flag[b] != 0;   // value * mask is not value here
+    const int any_bad = team.sync_or(nonfinite | (masked ? 1 : 0));
     int redo = any_bad;
     if (kCluster) {
         if (any_bad && tid == 0)
@@ -640,7 +645,8 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
             const float *val = p.value + (int64_t)b * p.value_stride_b;
             exact_sweep_cta0(team, val, p.value_stride_x, col, ptx::smem_u32(bits_s),
                              bits_smem ? nullptr : p.ws_bits + (size_t)b * K * plan.nblk * rows, rows, plan.nblk, tx, ty,
-                             p.max_neg_val);
+                             p.max_neg_val, masked ? p.mask + (int64_t)b * p.mask_stride_b : nullptr, p.mask_stride_x,
+                             p.mask_stride_y);
             if (!bits_smem) __threadfence();
         }
         if (kCluster)
@@ -709,16 +715,15 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
 // host helpers shared by the launchers
 // ---------------------------------------------------------------------------------------------
 inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // resolved once (C++11 magic static: thread-safe)
+    static const PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
         void *ptr = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-    }
+            return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+        return static_cast<PFN_cuTensorMapEncodeTiled_v12000>(nullptr);
+    }();
     return fn;
 }
 

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128) scatter_kernel(const float *__restrict__ 
     const int n = du[x], y0 = s_start[x];
     const float *row = dz + ((int64_t)b * D + d) * T_y;
     float acc = 0.f;
-    for (int k = 0; k < n; ++k) acc += __ldg(row + y0 + k);   // ascending frames: deterministic
+    for (int k = 0; k < n && y0 + k < T_y; ++k) acc += __ldg(row + y0 + k);   // ascending frames: deterministic
     dx[((int64_t)b * D + d) * T_x + x] = acc;
 }
 

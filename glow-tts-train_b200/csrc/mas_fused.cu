@@ -233,7 +233,7 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
     pp.T_x = T_x;
     pp.T_y = T_y;
     pp.max_neg_val = max_neg_val;
-    pp.dbg_cycles = g_dbg_cycles;
+    pp.dbg_cycles = g_dbg_cycles.load();
 
     CUtensorMap tmap;
     const cuuint64_t gdim[3] = {(cuuint64_t)T_y, (cuuint64_t)T_x, (cuuint64_t)B};

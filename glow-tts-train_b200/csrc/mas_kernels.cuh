@@ -1,6 +1,8 @@
 // mas_kernels.cuh -- parameter blocks and launchers shared by the C-ABI layer (mas_api.cu).
 #pragma once
 
+#include <atomic>
+
 #include "mas_common.cuh"
 
 namespace mas {
@@ -17,6 +19,7 @@ struct PathParams {
     int32_t *frame_token;  // nullable
     uint32_t *ws_bits;     // workspace: packed direction bits [B][ceil(T_y/32)][T_x]
     int32_t *ws_tok;       // workspace: frame -> token [B][T_y] when frame_token is null
+    const int *exact_flag; // nullable: [B], non-zero = compute this utterance from value * mask literally (mas_mask.cu)
     int B, T_x, T_y;
     float max_neg_val;
     long long *dbg_cycles;  // profiling hook (mas_b200_debug_set_cycle_buffer): [B][16 warps][16] clock64 stamps, or null
@@ -31,6 +34,31 @@ struct LogpParams {
     // (core.pyx:18) are never read by the sweep, so the producers do not contract them.
     const int32_t *x_len = nullptr, *y_len = nullptr;
 };
+
+// Per-device facts the launchers need, queried once per device under a lock (mas_api.cu).
+struct DeviceInfo {
+    int max_smem_optin;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
+    int num_sms;          // cudaDevAttrMultiProcessorCount
+};
+int get_device_info(int dev, DeviceInfo &out);   // MAS_OK or an error status; dev in [0, 64)
+
+// "the opt-in shared-memory attribute of this kernel has been raised to N bytes on device d": the
+// attribute is sticky, so it is only raised; concurrent callers may both raise it, which is harmless.
+struct SmemOptIn {
+    std::atomic<int> bytes[64];
+    template <typename Kernel>
+    int ensure(Kernel kern, int dev, int need) {
+        if (need > bytes[dev & 63].load(std::memory_order_acquire)) {
+            MAS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            int seen = bytes[dev & 63].load();
+            while (seen < need && !bytes[dev & 63].compare_exchange_weak(seen, need)) {}
+        }
+        return MAS_OK;
+    }
+};
+
+size_t mask_flag_bytes(int B);
+int launch_mask_check(const PathParams &p, int *flags, cudaStream_t stream);
 
 size_t path_simple_workspace_bytes(int B, int T_x, int T_y);
 int launch_path_simple(PathParams p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -57,7 +85,7 @@ int launch_mle_loss_backward(const float *z, const float *x_m, const float *x_lo
                              int T_x, int T_y, cudaStream_t stream);
 
 // developer profiling hook: when non-null, kernels stamp clock64() phase times into it
-extern long long *g_dbg_cycles;
+extern std::atomic<long long *> g_dbg_cycles;
 
 int launch_logp(const LogpParams &p, cudaStream_t stream);
 

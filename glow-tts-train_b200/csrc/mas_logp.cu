@@ -115,25 +115,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) mas_logp_kernel(LogpParams p,
 int launch_logp(const LogpParams &p, cudaStream_t stream) {
     using namespace logp;
     if (p.B == 0 || p.T_x == 0 || p.T_y == 0) return MAS_OK;
-    static int num_sms_cached[64] = {0}, configured[64] = {0};
+    static SmemOptIn optin;
     int dev = 0;
     MAS_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return MAS_ERR_INVALID_ARGUMENT;
-    if (num_sms_cached[dev] == 0)
-        MAS_CUDA_TRY(cudaDeviceGetAttribute(&num_sms_cached[dev], cudaDevAttrMultiProcessorCount, dev));
+    DeviceInfo di{};
+    if (int rc = get_device_info(dev, di)) return rc;
+    const int num_sms = di.num_sms;
     Geometry g{};
     g.t = make_tile_shape(p.T_x, p.T_y);
     g.panel = p.D < kPanel ? p.D : kPanel;
     g.generic = (p.D > kPanel) || (p.T_y & 3) || (reinterpret_cast<uintptr_t>(p.z) & 15) || (reinterpret_cast<uintptr_t>(p.logp) & 15);
     const int BT = p.B * g.t.row_tiles;
     const int64_t units = (int64_t)BT * g.t.nchunks;
-    const int P = (int)(units < num_sms_cached[dev] ? units : num_sms_cached[dev]);
+    const int P = (int)(units < num_sms ? units : num_sms);
     g.deal = make_deal(P, BT, g.t.nchunks);
     g.smem_bytes = cta_smem_floats(g.panel, g.t) * 4;
-    if (g.smem_bytes > configured[dev]) {
-        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_logp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
-        configured[dev] = g.smem_bytes;
-    }
+    if (int rc = optin.ensure(mas_logp_kernel, dev, g.smem_bytes)) return rc;
     mas_logp_kernel<<<P, kGemmThreads, g.smem_bytes, stream>>>(p, g);
     MAS_CUDA_TRY(cudaGetLastError());
     return MAS_OK;

@@ -76,6 +76,8 @@ mas_path_simple_kernel(PathParams p, int tile_w, int bits_in_smem) {
 
     const float neg = p.max_neg_val;
     const float *val = p.value + (int64_t)b * p.value_stride_b;
+    // utterances whose mask is not all-ones on the valid rectangle (mas_mask.cu): value * mask, literally
+    const float *msk = (p.exact_flag != nullptr && p.exact_flag[b] != 0) ? p.mask + (int64_t)b * p.mask_stride_b : nullptr;
     const int pitch = tile_w + 1;
 
     for (int x = tid; x < T_x; x += kThreads) {
@@ -93,7 +95,9 @@ mas_path_simple_kernel(PathParams p, int tile_w, int bits_in_smem) {
         const int w = min(tile_w, ty - y0);
         for (int i = tid; i < tx * tile_w; i += kThreads) {
             const int x = i / tile_w, j = i - x * tile_w;
-            tile[x * pitch + j] = (j < w) ? val[(int64_t)x * p.value_stride_x + y0 + j] : 0.f;
+            float v = (j < w) ? val[(int64_t)x * p.value_stride_x + y0 + j] : 0.f;
+            if (msk != nullptr && j < w) v *= msk[(int64_t)x * p.mask_stride_x + (int64_t)(y0 + j) * p.mask_stride_y];
+            tile[x * pitch + j] = v;
         }
         __syncthreads();
         for (int j = 0; j < w; ++j) {

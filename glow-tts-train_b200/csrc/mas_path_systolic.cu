@@ -49,7 +49,7 @@ mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p,
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int g_force_cluster = 0;   // testing hook (mas_b200_debug_force_cluster): 0 = heuristic
+static std::atomic<int> g_force_cluster{0};   // testing hook (mas_b200_debug_force_cluster): 0 = heuristic
 
 // The whole launch geometry: CTAs per utterance, warp shape, ring depth, where the direction bits go.
 static bool choose_plan(int B, int T_x, int T_y, int max_smem, int num_sms, Plan &best) {
@@ -66,7 +66,8 @@ static bool choose_plan(int B, int T_x, int T_y, int max_smem, int num_sms, Plan
             }
         return 0;
     };
-    if (g_force_cluster > 0) return try_k(g_force_cluster, best) != 0;
+    const int forced = g_force_cluster.load();
+    if (forced > 0) return try_k(forced, best) != 0;
     // Measured on B200 (profiles/sweep_k.py): one CTA per utterance wins whenever it fits with the
     // direction bits in shared memory (a DSMEM hop costs more than it buys); more CTAs per
     // utterance only pay for CAPACITY -- long texts whose boxes or bits do not fit one SM -- and
@@ -89,17 +90,14 @@ static bool choose_plan(int B, int T_x, int T_y, int max_smem, int num_sms, Plan
 
 template <int R, int kThreads>
 static int launch_rt(const CUtensorMap &tmap, const PathParams &p, const Plan &plan, cudaStream_t stream) {
-    static int configured_smem[64][4] = {{0}};        // opt-in attribute is sticky per device: raise it only when needed
+    static SmemOptIn optin[4];                        // opt-in attribute is sticky per device: raise it only when needed
     int dev = 0;
     MAS_CUDA_TRY(cudaGetDevice(&dev));
     const bool dbgk = p.dbg_cycles != nullptr;        // profiling build of the same kernel (clock64 stamps)
     const bool clus = plan.K > 1;
     auto kern = clus ? (dbgk ? mas_path_systolic_kernel<R, kThreads, true, true> : mas_path_systolic_kernel<R, kThreads, false, true>)
                      : (dbgk ? mas_path_systolic_kernel<R, kThreads, true, false> : mas_path_systolic_kernel<R, kThreads, false, false>);
-    if (plan.total > configured_smem[dev & 63][dbgk * 2 + clus]) {
-        MAS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.total));
-        configured_smem[dev & 63][dbgk * 2 + clus] = plan.total;
-    }
+    if (int rc = optin[dbgk * 2 + clus].ensure(kern, dev, plan.total)) return rc;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(p.B * plan.K));
     cfg.blockDim = dim3((unsigned)((plan.W + 1) * 32));
@@ -124,7 +122,7 @@ static int launch_r(const CUtensorMap &tmap, const PathParams &p, const Plan &pl
 
 }  // namespace systolic
 
-void path_systolic_force_cluster(int k) { systolic::g_force_cluster = k; }
+void path_systolic_force_cluster(int k) { systolic::g_force_cluster.store(k); }
 
 // Host-only: the plan the launcher would pick on a device with `max_smem` bytes of opt-in shared
 // memory per CTA and `num_sms` SMs.  out8 = {R, W, S, K, rows, nblk, bits_in_smem, total bytes}.
@@ -160,17 +158,13 @@ int launch_path_systolic(PathParams p, void *workspace, size_t workspace_bytes, 
     PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode_fn();
     if (encode == nullptr) return MAS_ERR_UNSUPPORTED_SHAPE;
 
-    static int max_smem_cached[64] = {0}, num_sms_cached[64] = {0};
     int dev = 0;
     MAS_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return MAS_ERR_INVALID_ARGUMENT;
-    if (max_smem_cached[dev] == 0) {
-        MAS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem_cached[dev], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        MAS_CUDA_TRY(cudaDeviceGetAttribute(&num_sms_cached[dev], cudaDevAttrMultiProcessorCount, dev));
-    }
-    const int max_smem = max_smem_cached[dev] - 2048;   // static shared + alignment slack
+    DeviceInfo di{};
+    if (int rc = get_device_info(dev, di)) return rc;
+    const int max_smem = di.max_smem_optin - 2048;   // static shared + alignment slack
     Plan plan{};
-    if (!choose_plan(p.B, p.T_x, p.T_y, max_smem, num_sms_cached[dev], plan)) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (!choose_plan(p.B, p.T_x, p.T_y, max_smem, di.num_sms, plan)) return MAS_ERR_UNSUPPORTED_SHAPE;
     if (!plan.bits_in_smem) {
         const size_t need = (size_t)p.B * plan.K * plan.nblk * plan.rows * 4;
         if (workspace == nullptr || workspace_bytes < need) return MAS_ERR_WORKSPACE_TOO_SMALL;

@@ -19,14 +19,15 @@ from .. import alignment
 __all__ = ["maximum_path"]
 
 
-def maximum_path(value, mask, *, assume_prefix_mask: bool = True):
-    """value: [b, t_x, t_y] scores, mask: [b, t_x, t_y] (models.py:334-337 prefix mask).
+def maximum_path(value, mask):
+    """value: [b, t_x, t_y] scores, mask: [b, t_x, t_y] (models.py:334-337 builds a prefix mask).
 
-    ``assume_prefix_mask=True`` (the only kind the reference ever builds) reads just row 0 and
-    column 0 of the mask, on the device, to get the valid sizes (__init__.py:18-19); the product
-    ``value * mask`` (__init__.py:11) is an identity on every cell the algorithm touches then.
-    Pass ``False`` for masks with interior zeros to apply the product first, exactly as the
-    reference does.
+    Same results as the reference for ANY mask: the valid sizes come from the mask's first column
+    and first row (__init__.py:18-19), read on the device; the product ``value * mask``
+    (__init__.py:11) is an identity on every cell the algorithm touches when the mask is all ones
+    on its valid rectangle -- the kernel entry verifies exactly that on the device (one pass over
+    the mask) and computes any other utterance from ``value * mask`` literally.  No host
+    synchronisation either way.
 
     CPU tensors are accepted for parity with the reference's device-agnostic signature: they are
     staged through the current CUDA device (pinned if they are pinned) and the result is copied
@@ -42,11 +43,10 @@ def maximum_path(value, mask, *, assume_prefix_mask: bool = True):
 
     scores = value.detach()
     mask = mask.detach()
-    if not assume_prefix_mask:
-        scores = scores * mask                              # __init__.py:11
     if on_host:
-        # lengths from the (small) first row / column on the host side of the copy; the full mask
-        # never crosses PCIe
+        # the product on the host side of the copy (the full mask never crosses PCIe), lengths from
+        # the (small) first row / column
+        scores = scores * mask                              # __init__.py:11
         t_x = mask[:, :, 0].sum(1).to(torch.int32).to(work_dev, non_blocking=True)   # __init__.py:18
         t_y = mask[:, 0, :].sum(1).to(torch.int32).to(work_dev, non_blocking=True)   # __init__.py:19
         scores = scores.to(work_dev, dtype=torch.float32, non_blocking=True)         # __init__.py:14
@@ -55,12 +55,12 @@ def maximum_path(value, mask, *, assume_prefix_mask: bool = True):
         out.copy_(path, non_blocking=False)                                            # __init__.py:21
         return out
 
-    scores = scores.to(torch.float32)                       # __init__.py:14 (.astype(np.float32))
-    if mask.dtype == torch.float32 and mask.device == device and mask.shape == scores.shape:
-        path = alignment.maximum_path_from_lengths(scores, mask=mask)
-    else:
-        mask = mask.to(device)
-        t_x = mask[:, :, 0].sum(1).to(torch.int32)          # __init__.py:18
-        t_y = mask[:, 0, :].sum(1).to(torch.int32)          # __init__.py:19
-        path = alignment.maximum_path_from_lengths(scores, t_x, t_y)
+    if tuple(mask.shape) != tuple(scores.shape):
+        mask = mask.expand_as(scores)
+    if scores.dtype != torch.float32:
+        # the reference forms value * mask in value's dtype BEFORE .astype(np.float32) (__init__.py:11,14):
+        # for half-precision scores keep that order
+        scores = (scores * mask.to(device=device, dtype=scores.dtype)).to(torch.float32)
+    mask = mask.to(device=device, dtype=torch.float32)      # a no-op for the fp32 view models.py:379 passes
+    path = alignment.maximum_path_from_lengths(scores, mask=mask)
     return path if dtype == torch.float32 else path.to(dtype)   # __init__.py:21

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAS_B200_ABI_VERSION 1
+#define MAS_B200_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------- */
 #define MAS_OK 0
@@ -97,9 +97,13 @@ size_t mas_b200_fused_workspace_bytes(int B, int D, int T_x, int T_y);
  *              its private copy; there is no copy here).
  *   t_x, t_y   int32 [B] device, per-utterance valid sizes; or both NULL, in which case
  *   mask       [B][T_x][T_y] fp32 device (any strides, in elements) supplies them the reference's
- *              way: t_x[b] = sum_x mask[b,x,0], t_y[b] = sum_y mask[b,0,y] (__init__.py:18-19).
- *              Only that column/row of the mask is read: for the prefix masks models.py:334-337
- *              builds, value*mask equals value on every cell the algorithm touches.
+ *              way: t_x[b] = sum_x mask[b,x,0], t_y[b] = sum_y mask[b,0,y] (__init__.py:18-19), and
+ *              the scores are value*mask (__init__.py:11).  For the prefix masks models.py:334-337
+ *              builds the product equals value on every cell the algorithm touches; that is
+ *              VERIFIED on the device (one pass over the mask's valid rectangle, mas_mask.cu), and
+ *              utterances whose mask is anything else (interior zeros, fractional entries) are
+ *              computed from value*mask literally -- same result as the reference for any mask,
+ *              no host synchronisation.
  *   path       [B][T_x][T_y] fp32 device, contiguous: written completely (zeros and ones).
  *   durations  int32 [B][T_x] device or NULL: frames per token (row sums of path; models.py:393).
  *   frame_token int32 [B][T_y] device or NULL: token index of every frame, -1 for y >= t_y[b].
@@ -206,6 +210,9 @@ int mas_b200_mle_loss_backward_f32(const float *z, const float *x_m, const float
 int mas_b200_maximum_path_host_i32(int32_t *paths, const float *values, const int32_t *t_xs,
                                    const int32_t *t_ys, int B, int T_x, int T_y,
                                    float max_neg_val, int device);
+/* Releases the device staging buffers and the stream the host entry above keeps per device (the
+ * only state the library holds).  Call when no host entry is running; may be called repeatedly. */
+void mas_b200_shutdown(void);
 
 #ifdef __cplusplus
 }

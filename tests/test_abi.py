@@ -41,7 +41,7 @@ def test_library_is_sm100a_only(pkg):
 
 def test_version_and_status_strings(pkg):
     lib = pkg._lib.load()
-    assert lib.mas_b200_abi_version() == 1
+    assert lib.mas_b200_abi_version() == 2
     assert lib.mas_b200_status_string(0) == b"ok"
     assert lib.mas_b200_status_string(3) == b"workspace too small"
     assert lib.mas_b200_status_string(99) == b"unknown status"

@@ -66,13 +66,39 @@ def test_drop_in_signature_and_contract(pkg, oracle):
         assert got.dtype == dt
         want_dt = oracle.maximum_path(v.float().cpu().numpy(), t_x, t_y)
         assert np.array_equal(as_i32(got), want_dt)
-    # non-prefix mask: exact reference semantics on request
+    # non-prefix mask: the reference's value * mask semantics, by default (verified on the device)
     holes = attn_mask.squeeze(1).clone()
     holes[:, 3:9, 10:30] = 0
     holes[:, 0, :] = attn_mask.squeeze(1)[:, 0, :]
     holes[:, :, 0] = attn_mask.squeeze(1)[:, :, 0]
-    got = pkg.monotonic_align.maximum_path(value, holes, assume_prefix_mask=False)
+    got = pkg.monotonic_align.maximum_path(value, holes)
     assert torch.equal(got, oracle.reference_boundary(value, holes))
+
+
+@pytest.mark.parametrize("shape", [(6, 40, 160), (4, 37, 150), (3, 200, 1000)])
+def test_any_mask_matches_the_reference_wrapper(pkg, oracle, shape):
+    """monotonic_align/__init__.py:11,18-19 for masks that are NOT the prefix masks of models.py:334-337:
+    interior zeros, fractional entries, a hole in column 0 (shortens t_x), mixed with clean
+    utterances in the same batch -- the device-side check flags exactly the utterances whose
+    value * mask differs, and the result equals the reference wrapper run on the same tensors.
+    Shapes cover the TMA kernel (T_y % 4 == 0) and the generic one (150 frames)."""
+    B, T_x, T_y = shape
+    rng = np.random.default_rng(zlib.crc32(repr(shape).encode()))
+    t_x, t_y = ragged_lengths(rng, B, T_x, T_y)
+    value = torch.from_numpy((10 * rng.standard_normal(shape) - 100).astype(np.float32)).to(DEV)
+    mask = torch.from_numpy(prefix_mask(t_x, t_y, T_x, T_y)).to(DEV)
+    m = mask.clone()
+    m[0, 2:5, 7:20] = 0                                  # interior zeros
+    if B > 1:
+        m[1, 1:, 3:9] = 0.5                              # fractional entries (scores are halved there)
+    if B > 2:
+        m[2, int(t_x[2]) - 1, :] = 0                     # last valid token masked out everywhere: t_x shrinks by one
+    # utterances 3.. stay clean prefix masks
+    got = pkg.monotonic_align.maximum_path(value, m)
+    want = oracle.reference_boundary(value, m)
+    assert torch.equal(got, want)
+    # and the clean batch still takes the fast path with identical results
+    assert torch.equal(pkg.monotonic_align.maximum_path(value, mask), oracle.reference_boundary(value, mask))
 
 
 def test_cpu_tensors_are_staged_not_computed_on_host(pkg, oracle):
