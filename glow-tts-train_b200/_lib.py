@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "mas_b200_debug_tile_shape",
     "mas_b200_debug_path_plan",
     "mas_b200_debug_deal",
+    "mas_b200_debug_fused_geom",
     "mas_b200_workspace_bytes",
     "mas_b200_fused_workspace_bytes",
     "mas_b200_maximum_path_f32",
@@ -72,6 +73,8 @@ def load() -> ctypes.CDLL:
     lib.mas_b200_debug_path_plan.argtypes = [_i32, _i32, _i32, _i32, _i32, _vp]
     lib.mas_b200_debug_deal.restype = _i32
     lib.mas_b200_debug_deal.argtypes = [_i32, _i32, _i32, _vp, _vp]
+    lib.mas_b200_debug_fused_geom.restype = _i32
+    lib.mas_b200_debug_fused_geom.argtypes = [_i32, _i32, _i32, _i32, _i32, _i32, _vp]
     lib.mas_b200_debug_force_unfused.restype = None
     lib.mas_b200_debug_force_unfused.argtypes = [_i32]
     lib.mas_b200_workspace_bytes.restype = _sz

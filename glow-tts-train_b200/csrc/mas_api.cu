@@ -235,6 +235,11 @@ int mas_b200_debug_path_plan(int B, int T_x, int T_y, int max_smem, int num_sms,
     return debug_path_plan(B, T_x, T_y, max_smem, num_sms, out8) ? MAS_OK : MAS_ERR_UNSUPPORTED_SHAPE;
 }
 
+int mas_b200_debug_fused_geom(int B, int D, int T_x, int T_y, int max_smem, int num_sms, int32_t *out12) {
+    if (B <= 0 || D <= 0 || T_x <= 0 || T_y <= 0 || max_smem <= 0 || num_sms <= 0 || !out12) return MAS_ERR_INVALID_ARGUMENT;
+    return debug_fused_geom(B, D, T_x, T_y, max_smem, num_sms, out12) ? MAS_OK : MAS_ERR_UNSUPPORTED_SHAPE;
+}
+
 int mas_b200_debug_deal(int P, int BT, int nchunks, int32_t *owner, int32_t *order) { return debug_deal(P, BT, nchunks, owner, order); }
 
 int mas_b200_debug_tile_shape(int T_x, int T_y, int32_t *out6) {

@@ -200,40 +200,51 @@ __device__ __forceinline__ void sweep_block(uint32_t tile, const uint32_t (&lane
     }
 }
 
-// Exact compare/select sweep for utterances whose scores are not all finite (NaN / +-inf): CTA 0
-// of the cluster walks the frames for ALL tokens with a barrier per frame, score column in shared
-// memory, scores read straight from global memory.  Slow, rare, and literal: core.pyx:17-30 as
-// written.  col: [2][tx] floats.  The direction words go where the fast sweep would have put
-// them: word (cb, x) belongs to CTA x / rows, in its shared memory (bits_smem_addr, written over
-// DSMEM) or in the workspace (bits_g, [K][nblk][rows]).
+// Exact compare/select sweep for utterances whose scores are not all finite (NaN / +-inf) or whose
+// mask is not all-ones (mas_mask.cu): CTA 0 of the cluster walks the frames for ALL tokens with a
+// barrier per frame, score column in shared memory, scores read straight from global memory.
+// Slow, rare, and literal: core.pyx:17-30 as written.  col: [2][tx] floats.  The direction words go
+// where the fast sweep would have put them: word (cb, x) belongs to CTA x / rows, in its shared
+// memory (bits_smem_addr, written over DSMEM) or in global memory (bits_g, [K][nblk][rows]).
 // msk: null, or the utterance's mask (element strides ms_x, ms_y): the scores are then value * mask
-// as monotonic_align/__init__.py:11 forms them (utterances flagged by mas_mask.cu).
-static __device__ __noinline__ void exact_sweep_cta0(const Team team, const float *__restrict__ val, int64_t stride_x, float *col,
-                                                     uint32_t bits_smem_addr, uint32_t *bits_g, int rows, int nblk, int tx, int ty,
-                                                     float neg, const float *__restrict__ msk = nullptr, int64_t ms_x = 0,
-                                                     int64_t ms_y = 0) {
-    const int tid = team.tid, nthr = team.nthr;
-    for (int x = tid; x < tx; x += nthr) col[x] = neg;
+// as monotonic_align/__init__.py:11 forms them.
+// Frames [y_begin, y_end) of the sweep; `buf` = which half of `col` holds the scores after frame
+// y_begin - 1 (exact_sweep_init sets half 0).  kCoherent: `val` was written by this CTA during this
+// launch (the single launch's redo scratch): plain loads instead of the read-only path.
+struct ExactBits {
+    uint32_t smem_addr;      // shared::cta address of this CTA's bit table (used when g == nullptr)
+    uint32_t *g;             // global bit table [K][nblk][rows], or nullptr
+    int rows, nblk;
+};
+__device__ __forceinline__ void exact_sweep_init(const Team team, float *col, int tx, float neg) {
+    for (int x = team.tid; x < tx; x += team.nthr) col[x] = neg;
     team.sync();
-    int buf = 0;
-    for (int y = 0; y < ty; ++y) {
+}
+template <bool kCoherent>
+static __device__ __noinline__ void exact_sweep_frames(const Team team, const float *val, int64_t stride_x, float *col, int &buf,
+                                                       const ExactBits eb, int tx, int y_begin, int y_end, float neg,
+                                                       const float *__restrict__ msk = nullptr, int64_t ms_x = 0,
+                                                       int64_t ms_y = 0) {
+    const int tid = team.tid, nthr = team.nthr;
+    for (int y = y_begin; y < y_end; ++y) {
         const float *vin = col + buf * tx;
         float *vout = col + (buf ^ 1) * tx;
         for (int x = tid; x < tx; x += nthr) {
             const float stay = vin[x];                                      // == -1e9 while x > y-1, core.pyx:19-20
             const float adv = (x == 0) ? ((y == 0) ? 0.f : neg) : vin[x - 1];   // core.pyx:23-29
-            float l = (x > y) ? 0.f : __ldg(val + (int64_t)x * stride_x + y);
+            const float *vp = val + (int64_t)x * stride_x + y;
+            float l = (x > y) ? 0.f : (kCoherent ? *reinterpret_cast<const volatile float *>(vp) : __ldg(vp));
             if (msk != nullptr && x <= y) l *= __ldg(msk + (int64_t)x * ms_x + (int64_t)y * ms_y);
             const bool take = adv > stay;
             vout[x] = (take ? adv : stay) + l;
             const uint32_t bit = ((take || (x == y && x > 0)) ? 1u : 0u) << (y & 31);
-            const int owner = x / rows, xl = x - owner * rows;
-            const size_t word = (size_t)(y >> 5) * rows + xl;
-            if (bits_g == nullptr) {
-                const uint32_t addr = ptx::mapa(bits_smem_addr + (uint32_t)word * 4u, owner);
+            const int owner = x / eb.rows, xl = x - owner * eb.rows;
+            const size_t word = (size_t)(y >> 5) * eb.rows + xl;
+            if (eb.g == nullptr) {
+                const uint32_t addr = ptx::mapa(eb.smem_addr + (uint32_t)word * 4u, owner);
                 ptx::st_cluster_u32(addr, ((y & 31) ? ptx::ld_cluster_u32(addr) : 0u) | bit);
             } else {
-                uint32_t *w = bits_g + (size_t)owner * nblk * rows + word;
+                uint32_t *w = eb.g + (size_t)owner * eb.nblk * eb.rows + word;
                 __stcg(w, ((y & 31) ? __ldcg(w) : 0u) | bit);
             }
         }
@@ -295,14 +306,10 @@ __device__ __forceinline__ int backtrack_tokens(const uint32_t *bits, int rows, 
 
 // The whole per-CTA program of kernel (1): lengths, sweep, (exact redo), backtrack, dense output.
 // kCluster: compiled with the distributed-shared-memory paths (K > 1); the K == 1 build carries none.
-// kFused: the scores are produced by other CTAs of the same launch (mas_fused.cu) in chunks of
-// `chunk_frames` frames: every box load first waits for the ready flags of the chunks it reads
-// (`ready[chunk] >= ready_target`, acquire at GPU scope, then a proxy fence before the TMA read).
 // `b`: utterance; `cta_tag`: index for the profiling buffer; warps beyond plan.W + 1 idle.
-template <int R, bool kDbg, bool kCluster, bool kFused>
+template <int R, bool kDbg, bool kCluster>
 __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams &p, const Plan &plan, unsigned char *smem,
-                                       int b, int cta_tag, const int *ready, int ready_target, int chunk_frames = 64,
-                                       int nchunks = 0, const Team team = whole_cta()) {
+                                       int b, int cta_tag, const Team team = whole_cta()) {
     float *s_len = reinterpret_cast<float *>(smem + plan.off_misc + 16);
 
     const int K = kCluster ? plan.K : 1;
@@ -564,8 +571,8 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         // (1) zero this CTA's slice of the dense output with bulk async copies of a shared zero page
         //     (UBLKCP: a few dozen instructions for the whole slab instead of a flood of vector
         //     stores that would compete with the sweep warps for the load/store pipe);
-        // (2) feed every sweep warp's ring: wait for a slot to be handed back (`empty`), in the fused
-        //     launch also for the producers' ready flag of the chunk, arm `full`, issue the TMA box.
+        // (2) feed every sweep warp's ring: wait for a slot to be handed back (`empty`), arm `full`,
+        //     issue the TMA box.
         float4 *zero4 = reinterpret_cast<float4 *>(smem + plan.off_zero);
         for (int i = lane; i < plan.zero_bytes / 16; i += 32) zero4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         ptx::fence_proxy_async();                              // generic writes -> visible to the async proxy
@@ -592,20 +599,14 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                 if (want) {
                     const int sl = k % S;
                     // a slot's n-th reuse waits for its n-th hand-back; the first S boxes need none
-                    go = k < S || ptx::mbar_test_wait(&empty[lane * S + sl], (uint32_t)(((k / S) & 1) ^ 1));
-                    if (kFused && go) {
-                        // the box spans frames [f0, f0 + 32): one or two of the producers' chunks
-                        const int f0 = (w_cb0 + k) * kBlk;
-                        const int c0 = f0 / chunk_frames, c1 = min((f0 + kBlk - 1) / chunk_frames, nchunks - 1);
-                        go = ptx::ld_acquire_gpu(ready + c0) >= ready_target;
-                        if (go && c1 != c0) go = ptx::ld_acquire_gpu(ready + c1) >= ready_target;
-                        if (go) ptx::fence_proxy_async_all();
-                    }
-                    if (go) {
+                    bool ok = k < S || ptx::mbar_test_wait(&empty[lane * S + sl], (uint32_t)(((k / S) & 1) ^ 1));
+                    const int f0 = (w_cb0 + k) * kBlk;
+                    if (ok) {
                         float *dst = ring + ((size_t)lane * S + sl) * (rows_per_warp * kBlk);
                         ptx::mbar_arrive_expect_tx(&full[lane * S + sl], box_bytes);
-                        ptx::tma_load_3d(dst, &tmap, &full[lane * S + sl], (w_cb0 + k) * kBlk, wx0, b);
+                        ptx::tma_load_3d(dst, &tmap, &full[lane * S + sl], f0, wx0, b);
                         ++k;
+                        go = true;
                     }
                 }
                 if (zoff < ztotal) {
@@ -629,7 +630,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
     }
     if (!bits_smem) __threadfence();
     // ---- were all scores finite?  (cluster-wide) ----
-    const bool masked = !kFused && p.exact_flag != nullptr && p.exact_flag[b] != 0;   // value * mask is not value here
+    const bool masked = p.exact_flag != nullptr && p.exact_flag[b] != 0;   // value * mask is not value here
     const int any_bad = team.sync_or(nonfinite | (masked ? 1 : 0));
     int redo = any_bad;
     if (kCluster) {
@@ -638,15 +639,20 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         ptx::cluster_sync();
         redo = misc[3];
     }
+    bool bits_from_smem = bits_smem;
     if (redo) {
-        // non-finite scores: the sign trick is not the reference's compare there -- redo literally
+        // non-finite scores (or a mask that is not all-ones): the sign trick is not the reference's
+        // compare there -- redo literally
         if (c == 0) {
             float *col = reinterpret_cast<float *>(smem + plan.off_ring);
             const float *val = p.value + (int64_t)b * p.value_stride_b;
-            exact_sweep_cta0(team, val, p.value_stride_x, col, ptx::smem_u32(bits_s),
-                             bits_smem ? nullptr : p.ws_bits + (size_t)b * K * plan.nblk * rows, rows, plan.nblk, tx, ty,
-                             p.max_neg_val, masked ? p.mask + (int64_t)b * p.mask_stride_b : nullptr, p.mask_stride_x,
-                             p.mask_stride_y);
+            const ExactBits eb{ptx::smem_u32(bits_s), bits_smem ? nullptr : p.ws_bits + (size_t)b * K * plan.nblk * rows, rows,
+                               plan.nblk};
+            int buf = 0;
+            exact_sweep_init(team, col, tx, p.max_neg_val);
+            exact_sweep_frames<false>(team, val, p.value_stride_x, col, buf, eb, tx, 0, ty, p.max_neg_val,
+                                      masked ? p.mask + (int64_t)b * p.mask_stride_b : nullptr, p.mask_stride_x,
+                                      p.mask_stride_y);
             if (!bits_smem) __threadfence();
         }
         if (kCluster)
@@ -675,8 +681,8 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         }
         const int x_min = max(xc, 1);
         if (x >= x_min)
-            y_hi = bits_smem ? backtrack_tokens<true>(bits_s, rows, xc, x, y_hi, x_min, run)
-                             : backtrack_tokens<false>(bits_g, rows, xc, x, y_hi, x_min, run);
+            y_hi = bits_from_smem ? backtrack_tokens<true>(bits_s, rows, xc, x, y_hi, x_min, run)
+                                  : backtrack_tokens<false>(bits_g, rows, xc, x, y_hi, x_min, run);
         if (!kCluster || c == 0) {
             run[0] = make_int2(0, y_hi);
         } else {

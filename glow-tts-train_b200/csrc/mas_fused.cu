@@ -1,25 +1,36 @@
-// mas_fused.cu -- kernel (2): log-likelihood + alignment search in ONE launch (models.py:362-382).
+// mas_fused.cu -- kernel (2): log-likelihood + alignment search in ONE launch (models.py:362-382),
+// any batch size, the [B,T_x,T_y] score matrix never materialised -- not in HBM, not in L2: every
+// score is produced and consumed inside one SM's shared memory.
 //
-// One CTA per SM, two kinds sharing the grid and running concurrently:
-//   * producers (blockIdx < P): the FFMA contraction of mas_logp_cta.cuh, 16 warps, a token tile of
-//     one utterance resident in shared memory, walking chunks in an interleaved order (Deal:
-//     producer j of the d on a tile takes chunks j, j+d, ...) so that the scores of EARLY frames of
-//     every utterance exist first; after each chunk is stored they raise that chunk's ready flag
-//     (fence + red.release.gpu);
-//   * one sweep CTA per utterance: kernel (1)'s program (mas_dp_cta.cuh) whose loader warp waits for
-//     the flags of the chunks a TMA box reads (ld.acquire.gpu + fence.proxy.async), so the systolic
-//     sweep trails the producers by a few blocks instead of starting after the last FFMA.
-// A sweep warp runs alone on its scheduler at ~0.45 IPC; sharing the SM with FFMA warps halved its
-// speed and made it the tail of the launch (profiles/r1_fused_timeline.txt, first layout), so a sweep
-// CTA now has its SM to itself: the shared-memory request is sized so that only one CTA fits.
-// Producers never wait for anybody and carry the lower block indices, so the launch cannot
-// deadlock whatever the residency.  With more utterances than a third of the SMs the two kernels
-// run back to back instead (the caller's fallback).
+// One thread-block CLUSTER of K CTAs per utterance (K = 1, 2, 4 or 8; persistent: cluster j takes
+// utterances j, 2 NC - 1 - j, 2 NC + j, ... of the batch).  The utterance's TOKENS are sliced over
+// the K CTAs (slice = ceil(t_x / K), by the utterance's actual length), and a CTA does everything
+// for its slice:
+//   * FFMA warps (15 of the 16) contract the slice's scores over the mel channels, chunk of F frames
+//     by chunk, into a SCORE RING in shared memory: boxes of [slice tokens x 32 frames] fp32 in the
+//     128-byte-swizzled layout kernel (1) stages with TMA.  The warps work in independent TEAMS with a
+//     named barrier each (chunk j belongs to team j mod nteams), so that finished scores appear every
+//     F frames instead of every nteams x F.  The token-side operands (-0.5 exp(-2 logs), m exp(-2 logs))
+//     stay in shared memory for the whole utterance; z arrives in panels of 16 channels by cp.async,
+//     double-buffered per team.  Arithmetic, operand order and the row constants' summation order are
+//     those of the materialising kernel (mas_logp_cta.cuh): bit-identical scores.
+//   * ONE sweep warp (warp 0) runs kernel (1)'s recurrence (mas_dp_cta.cuh: sweep_block) over the
+//     ring, 32 frames per step: waits for the teams' chunk counters (shared memory, acquire), takes the
+//     score of the slice's predecessor token from the previous CTA's sweep through distributed shared
+//     memory and hands its own last token's to the next CTA, packs the direction bits, frees the box
+//     (`consumed`, the producers' back-pressure), and drips bulk copies of a zero page into the dense
+//     output on the way.
+//   * backtrack by tokens, CTA K-1 -> 0 over DSMEM; ones, durations, frame -> token by all threads.
+// Only the cells the reference's band touches are ever contracted (core.pyx:18): a slice starts at
+// the 32-frame block of its first token and ends where its last token leaves the band.
 //
-// The scores travel through a [B,T_x,T_y] fp32 scratch in the caller's workspace, written once and
-// read once while still in the 126 MB L2 (25.6 MB for B=32, 200x1000).
+// Utterances with a non-finite score (NaN / inf inputs) are detected by the sweep as in kernel (1)
+// and recomputed literally by CTA 0 of the cluster: scores chunk by chunk (the materialising
+// kernel's program) into a one-chunk scratch, compare/select sweep, direction bits in the workspace.
+//
+// Shapes the launch does not take (frame count not a multiple of 4, more than 80 channels, slices
+// that do not fit an SM) run as the two kernels back to back over groups of utterances (mas_api.cu).
 #include <cuda.h>
-#include <cudaTypedefs.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -30,91 +41,762 @@
 namespace mas {
 namespace fused {
 
-constexpr int kThreads = kGemmThreads;          // producers: 16 warps | sweep CTAs use W + 1 of them
+using systolic::kBlk;
+using systolic::kBndBlocks;
+using systolic::kDoneAll;
+using systolic::kSpinLimit;
 
-struct Geometry {
-    int P;             // producer CTAs
-    TileShape t;
-    logp::Deal deal;
-    int *ready;        // [B][nchunks] chunk ready counters
-    int teams;         // utterances per sweep CTA: 2 (a half CTA each) when two plans fit one SM, else 1
-    int team_stride;   // bytes of shared memory per team
-    int head;          // chunks 0 .. head-1 of an utterance are produced by its own sweep CTA first
+constexpr int kThreads = 512;
+constexpr int kChan = 16;              // channels per staged panel of z
+constexpr int kZeroPage = 8192;        // bytes of zeros the dense output is filled from
+constexpr int kMaxTeams = 8;
+constexpr int kBarFfma = 15;           // named barrier of all FFMA threads; teams use 1 .. nteams
+constexpr int kMaxClusters = 192;      // workspace bound (no device query in the size function)
+
+// control words in shared memory (ints)
+enum Ctl { kTeamDone = 0, kConsumed = 8, kDonePrev = 9, kDoneSelf = 10, kDoneNext = 11, kBtFlag = 12, kBtToken = 13,
+           kBtFrame = 14, kRedo = 15, kCtlInts = 16 };
+
+struct Geom {
+    int K, NC;                         // CTAs per cluster, clusters in the grid
+    int ffma_all;                      // 15 FFMA warps (all but the sweep warp) or 12 (the sweep warp's scheduler stays free)
+    int nteams, team_warps;
+    int max_slice, tr_max, ring_rows;  // tokens per CTA (bound), the same rounded up to 4 / to 8
+    int CG_cap, F_cap;                 // column groups / frames per chunk (bound)
+    int NB;                            // score ring depth in 32-frame boxes
+    int nblk, bits_in_smem;
+    int nsh, dsh;                      // channel shares of the row constants, as the materialising kernel sums them
+    int off_zero, off_bnd, off_run, off_ctl, off_big, off_ops, off_l14, off_part, off_z, off_l2, off_ring, off_bits, total;
+    uint32_t *ws_bits;                 // [NC][K][nblk][ring_rows] when the bits do not fit shared memory
+    float *redo_scratch;               // [NC][T_x][t_ref.F]
+    uint32_t *redo_bits;               // [NC][nblk][T_x + 64]
+    TileShape t_ref;                   // the materialising kernel's tile (row-constant shares, redo)
 };
 
-template <int R, bool kDbg>
-__global__ void __launch_bounds__(kThreads, 1)
-mas_fused_kernel(const __grid_constant__ CUtensorMap tmap, PathParams pp, systolic::Plan plan, LogpParams lp, Geometry g) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    if ((int)blockIdx.x < g.P) {
-        // profiling: producers stamp globaltimer per chunk behind the sweep CTAs' [B][16][16] block
-        long long *dbg_ns = (kDbg && pp.dbg_cycles) ? pp.dbg_cycles + ((size_t)pp.B * 16 + blockIdx.x) * 16 : nullptr;
-        logp::run_deal<true>(lp, reinterpret_cast<float *>(smem), g.t, g.deal, blockIdx.x, g.ready, g.head, dbg_ns);
-    } else if (g.teams == 1) {
-        const int b = blockIdx.x - g.P;
-        // experiment hook (launch_fused): head chunks of the own utterance first
-        if (g.head > 0) {
-            for (int rt = 0; rt < g.t.row_tiles; ++rt)
-                logp::logp_cta<true>(lp, reinterpret_cast<float *>(smem), g.t, b, rt * g.t.tile_rows, 0, 1, g.head, 0x7fffffff, 0, 0,
-                                     g.ready + (size_t)b * g.t.nchunks, nullptr);
-            __syncthreads();                            // the shared memory changes hands
-            ptx::fence_proxy_async();                   // generic-proxy writes before the TMA boxes land there
+// One utterance as one CTA of its cluster sees it.
+struct Utt {
+    int b, tx, ty;
+    int c;                             // rank in the cluster
+    int n_c;                           // tokens per slice (multiple of R)
+    int x0, n_real;                    // first token / real tokens of this CTA's slice
+    int TR, RG, CG, F;                 // contraction tile: TR = 4 RG rows, chunks of F = 8 CG frames
+    int cb0, cbend;                    // 32-frame blocks the slice is in the band for (cbend < cb0: none)
+    int nch;                           // chunks to contract
+};
+
+__device__ __forceinline__ void named_sync(int bar, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthr) : "memory"); }
+__device__ __forceinline__ int ld_acquire_shared(const int *p) { return ptx::ld_acquire_shared_a(ptx::smem_u32(p)); }
+__device__ __forceinline__ void st_release_shared(int *p, int v) { ptx::st_release_shared_if_a(true, ptx::smem_u32(p), v); }
+
+// ---------------------------------------------------------------------------------------------
+// FFMA side
+// ---------------------------------------------------------------------------------------------
+
+// Token-side operands of the slice, by all FFMA threads (fidx of nffma).  The element-wise part is
+// spread over every thread; the row constants are summed the way mas_logp_cta.cuh::stage_tokens does
+// (nsh shares of dsh channels, ascending inside a share, shares added in order) from the same
+// expressions, so that they are bit-identical (the second pass re-reads its operands from L1).
+__device__ __forceinline__ void stage_ops(const Geom &g, const Utt &u, const LogpParams &p, unsigned char *smem, int fidx, int nffma) {
+    const int D = p.D, T_x = p.T_x, TR = u.TR;
+    float *sInv = reinterpret_cast<float *>(smem + g.off_ops), *sMiv = sInv + D * TR;
+    float *sL1 = reinterpret_cast<float *>(smem + g.off_l14), *sL4 = sL1 + g.tr_max;
+    float *sPart = reinterpret_cast<float *>(smem + g.off_part);
+    const float *xm = p.x_m + (int64_t)u.b * D * T_x + u.x0;
+    const float *xl = p.x_logs ? p.x_logs + (int64_t)u.b * D * T_x + u.x0 : nullptr;
+    for (int e = fidx; e < D * TR; e += nffma) {
+        const int d = e / TR, x = e - d * TR;
+        float inv = 0.f, miv = 0.f;
+        if (x < u.n_real) {
+            const float m = __ldg(xm + (int64_t)d * T_x + x);
+            const float ls = xl ? __ldg(xl + (int64_t)d * T_x + x) : 0.f;
+            const float r = xl ? expf(-2.0f * ls) : 1.0f;         // models.py:363
+            inv = -0.5f * r;                                        // models.py:368
+            miv = m * r;                                            // models.py:371
         }
-        systolic::dp_cta<R, kDbg, false, true>(tmap, pp, plan, smem, b, b, g.ready + (size_t)b * g.t.nchunks, g.t.row_tiles,
-                                               g.t.F, g.t.nchunks);
-    } else {
-        // two utterances per sweep CTA, half the threads and half the shared memory each, a hardware
-        // barrier of their own: the sweeps then hold B/2 SMs instead of B and the producers get the rest
-        constexpr int kTeam = kThreads / 2;
-        const int team = threadIdx.x / kTeam;
-        const int b = 2 * ((int)blockIdx.x - g.P) + team;
-        if (b >= pp.B) return;
-        systolic::dp_cta<R, kDbg, false, true>(tmap, pp, plan, smem + (size_t)team * g.team_stride, b, b,
-                                               g.ready + (size_t)b * g.t.nchunks, g.t.row_tiles, g.t.F, g.t.nchunks,
-                                               systolic::Team{(int)threadIdx.x - team * kTeam, kTeam, 1 + team});
+        sInv[e] = inv;
+        sMiv[e] = miv;
+    }
+    if (fidx < g.nsh * TR) {
+        const int h = fidx / TR, x = fidx - h * TR;
+        const int d0 = h * g.dsh, d1 = min(D, d0 + g.dsh);
+        float l1 = 0.f, l4 = 0.f;
+        if (x < u.n_real) {
+#pragma unroll 4
+            for (int d = d0; d < d1; ++d) {
+                const float m = __ldg(xm + (int64_t)d * T_x + x);
+                const float ls = xl ? __ldg(xl + (int64_t)d * T_x + x) : 0.f;
+                const float r = xl ? expf(-2.0f * ls) : 1.0f;
+                l1 += kNegHalfLog2Pi - ls;                          // models.py:364-366
+                l4 = fmaf(-0.5f * (m * m), r, l4);                  // models.py:373-375
+            }
+        }
+        sPart[(2 * h) * TR + x] = l1;
+        sPart[(2 * h + 1) * TR + x] = l4;
+    }
+    named_sync(kBarFfma, nffma);
+    if (fidx < TR) {
+        float l1 = sPart[fidx], l4 = sPart[TR + fidx];
+        for (int h = 1; h < g.nsh; ++h) {
+            l1 += sPart[(2 * h) * TR + fidx];
+            l4 += sPart[(2 * h + 1) * TR + fidx];
+        }
+        sL1[fidx] = l1;
+        sL4[fidx] = l4;
+    }
+    named_sync(kBarFfma, nffma);
+}
+
+// One team's share of the slice's chunks: chunk j = team, team + nteams, ...  ttid of tn threads.
+template <bool kMeanOnly>
+__device__ __forceinline__ void team_contract(const Geom &g, const Utt &u, const LogpParams &p, unsigned char *smem, int *ctl,
+                                              int team, int ttid, int tn) {
+    if (team >= u.nch) return;
+    const int D = p.D, T_y = p.T_y, F = u.F, CG = u.CG, TR = u.TR, NB = g.NB;
+    const float *sInv = reinterpret_cast<const float *>(smem + g.off_ops), *sMiv = sInv + D * TR;
+    const float *sL1 = reinterpret_cast<const float *>(smem + g.off_l14), *sL4 = sL1 + g.tr_max;
+    float *sZ = reinterpret_cast<float *>(smem + g.off_z) + (size_t)team * 2 * kChan * g.F_cap;   // [2][kChan][F]
+    float *sL2 = reinterpret_cast<float *>(smem + g.off_l2) + team * g.F_cap;
+    const uint32_t ring_a = ptx::smem_u32(smem + g.off_ring), box_bytes = (uint32_t)g.ring_rows * 128u;
+    const int bar = 1 + team;
+    const int rg = ttid / CG, cg = ttid - rg * CG;
+    const bool worker = rg < u.RG;
+    const float *zg = p.z + (int64_t)u.b * D * T_y;
+    const int f_begin = u.cb0 * kBlk;
+    const int total_rel = (u.cbend - u.cb0 + 1) * kBlk;     // frames the sweep reads, from f_begin
+    const int npan = ceil_div(D, kChan);
+    const int f4 = F >> 2;
+    const int *consumed = ctl + kConsumed;
+    auto stage = [&](int j, int pd, int buf) {
+        const int y0 = f_begin + j * F, d0 = pd * kChan, cnt = min(kChan, D - d0);
+        float *dst = sZ + buf * kChan * g.F_cap;
+        for (int i = ttid; i < cnt * f4; i += tn) {
+            const int d = i / f4, k4 = (i - d * f4) << 2, y = y0 + k4;
+            ptx::cp_async_16(dst + d * F + k4, zg + (int64_t)(d0 + d) * T_y + (y < T_y ? y : 0), y < T_y);
+        }
+        ptx::cp_async_commit();
+    };
+    int buf = 0, count = 0;
+    bool announce = false;                                  // the previous chunk's stores are not yet published
+    uint32_t spins = 0;
+    stage(team, 0, 0);
+    for (int j = team; j < u.nch; j += g.nteams) {
+        GemmAcc acc;
+#pragma unroll
+        for (int i = 0; i < kGemmTM; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc.v[i][q] = 0ull;
+        float l2 = 0.f;
+        for (int pd = 0; pd < npan; ++pd) {
+            if (pd == npan - 1 && ttid == 0) {
+                // back-pressure: the boxes this chunk is stored into must have been swept
+                const int bx_last = (min(total_rel, j * F + F) - 1) >> 5;
+                while (ld_acquire_shared(consumed) + NB <= bx_last) {
+                    __nanosleep(64);
+                    if (++spins > kSpinLimit) systolic::spin_fail();
+                }
+            }
+            ptx::cp_async_wait<0>();
+            named_sync(bar, tn);                            // the panel has landed; everyone is done with the other buffer
+            if (announce && ttid == 0) st_release_shared(ctl + kTeamDone + team, count);   // (stores ordered by the barrier)
+            announce = false;
+            if (pd + 1 < npan)
+                stage(j, pd + 1, buf ^ 1);
+            else if (j + g.nteams < u.nch)
+                stage(j + g.nteams, 0, buf ^ 1);
+            const float *zb = sZ + buf * kChan * g.F_cap;
+            const int d0 = pd * kChan, cnt = min(kChan, D - d0);
+            if (worker) {
+                if (cnt == kChan)
+                    gemm_tile_d<false, kChan, kMeanOnly>(sInv + d0 * TR, sMiv + d0 * TR, zb, cnt, TR, F, rg, cg, acc);
+                else
+                    gemm_tile_d<false, 0, kMeanOnly>(sInv + d0 * TR, sMiv + d0 * TR, zb, cnt, TR, F, rg, cg, acc);
+            }
+            if (kMeanOnly && ttid < F) {                    // models.py:367-369 with logs == 0: one sum per frame
+                for (int d = 0; d < cnt; ++d) {
+                    const float zv = zb[d * F + ttid];
+                    l2 = fmaf(-0.5f * zv, zv, l2);
+                }
+            }
+            buf ^= 1;
+        }
+        if (kMeanOnly) {
+            if (ttid < F) sL2[ttid] = l2;
+            named_sync(bar, tn);
+        }
+        if (worker) {
+            const int relb = j * F;
+#pragma unroll
+            for (int i = 0; i < kGemmTM; ++i) {
+                const int xr = rg * kGemmTM + i;
+                const float l1 = sL1[xr], l4 = sL4[xr];
+                const uint32_t row_a = ring_a + (uint32_t)xr * 128u;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int yl = (F >> 1) * h + 4 * cg, relf = relb + yl;
+                    if (relf >= total_rel) continue;        // beyond the last box the sweep reads
+                    float cq[4];
+                    acc.quad(i, h, cq);
+                    float4 r;
+                    if (kMeanOnly) {
+                        const float4 q2 = *reinterpret_cast<const float4 *>(sL2 + yl);
+                        r.x = logp_cell_finish_mean_only(l1, q2.x, cq[0], l4);
+                        r.y = logp_cell_finish_mean_only(l1, q2.y, cq[1], l4);
+                        r.z = logp_cell_finish_mean_only(l1, q2.z, cq[2], l4);
+                        r.w = logp_cell_finish_mean_only(l1, q2.w, cq[3], l4);
+                    } else {
+                        r.x = logp_cell_finish(l1, cq[0], l4);
+                        r.y = logp_cell_finish(l1, cq[1], l4);
+                        r.z = logp_cell_finish(l1, cq[2], l4);
+                        r.w = logp_cell_finish(l1, cq[3], l4);
+                    }
+                    const int bx = relf >> 5, slot = bx % NB, gq = (relf & 31) >> 2;
+                    ptx::st_shared_v4_if(true, row_a + (uint32_t)slot * box_bytes + (uint32_t)((gq ^ (xr & 7)) << 4), r);
+                }
+            }
+        }
+        ++count;
+        announce = true;
+    }
+    named_sync(bar, tn);
+    if (ttid == 0) st_release_shared(ctl + kTeamDone + team, count);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sweep side (one warp)
+// ---------------------------------------------------------------------------------------------
+
+// Cells below the diagonal (token > frame) of a staged box -> 0 (see systolic::zero_below_diagonal);
+// rows beyond the slice's tile are not touched.
+template <int R>
+__device__ __forceinline__ void zero_below_diagonal_rows(uint32_t tile_a, int lane, int row0, int col0, int nrows) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int q = lane * R + i;
+        const int d = row0 + i - col0;              // frames [0, d) of this block are below the diagonal
+        if (d <= 0 || q >= nrows) continue;
+        const uint32_t row_a = tile_a + (uint32_t)q * 128u;
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) {
+            if (4 * cidx >= d) break;
+            const uint32_t a = row_a + (uint32_t)((cidx ^ (q & 7)) << 4);
+            float4 x = ptx::ld_shared_v4(a);
+            x.x = 0.f;
+            if (4 * cidx + 1 < d) x.y = 0.f;
+            if (4 * cidx + 2 < d) x.z = 0.f;
+            if (4 * cidx + 3 < d) x.w = 0.f;
+            ptx::st_shared_v4_if(true, a, x);
+        }
     }
 }
 
+// The dense output's zeros: this CTA's share of the utterance's rows, dripped by lane 0 of the sweep
+// warp as bulk copies of the shared zero page.
+struct ZeroFill {
+    char *dst;
+    int64_t total, off;
+    int per_block;        // copies per sweep block
+    __device__ __forceinline__ void drip(const void *zero_page, int n) {
+        for (int i = 0; i < n && off < total; ++i) {
+            const int64_t left = total - off;
+            ptx::bulk_store_s2g(dst + off, zero_page, (uint32_t)(left < kZeroPage ? left : kZeroPage));
+            off += kZeroPage;
+        }
+    }
+};
+
+// Returns non-zero when a real token of the slice ended with a non-finite score.
+template <int R, bool kDbg>
+__device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned char *smem, int *ctl, float neg, ZeroFill &zf,
+                                           uint32_t *bits_g, long long *dbg) {
+    const int lane = threadIdx.x & 31;
+    const void *zero_page = smem + g.off_zero;
+    int nonfinite = 0;
+    if (u.cbend >= u.cb0) {
+        float v[R];
+        uint32_t acc[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) v[i] = neg;
+        float carry = (u.x0 == 0) ? 0.f : neg;              // frame 0 of token 0 starts from 0 (core.pyx:24-25)
+        const bool has_next = u.x0 + u.n_c < u.tx;          // the next CTA has real tokens
+        const bool publisher = has_next && lane == u.n_c / R - 1;   // owns the slice's last token (n_c % R == 0)
+        const uint32_t bnd_a = ptx::smem_u32(smem + g.off_bnd);
+        const uint32_t bnd_out_base = has_next ? ptx::mapa(bnd_a, (uint32_t)(u.c + 1)) : 0u;
+        const uint32_t done_prev_a = ptx::smem_u32(ctl + kDonePrev), done_next_a = ptx::smem_u32(ctl + kDoneNext);
+        // my consumption -> the previous CTA's `done next`; my production -> the next CTA's `done prev`
+        const uint32_t mirror_prev = (u.c > 0) ? ptx::mapa(done_next_a, (uint32_t)(u.c - 1)) : 0u;
+        const uint32_t mirror_next = has_next ? ptx::mapa(done_prev_a, (uint32_t)(u.c + 1)) : 0u;
+        int seen_prev = (u.c > 0) ? -1 : kDoneAll;
+        int seen_next = has_next ? -1 : kDoneAll;
+        const int row0 = u.x0 + lane * R;
+        const int x_last = u.x0 + u.n_real - 1;
+        uint32_t lane_c[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int row = min(lane * R + i, u.TR - 1);   // lanes beyond the tile re-read its last row (their tokens are inert)
+            lane_c[i] = (uint32_t)(row * 128) | (uint32_t)((row & 7) << 4);
+        }
+        const uint32_t ring_a = ptx::smem_u32(smem + g.off_ring), box_bytes = (uint32_t)g.ring_rows * 128u;
+        uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem + g.off_bits);
+        uint32_t *bits_p = (g.bits_in_smem ? bits_s : bits_g) + (size_t)u.cb0 * g.ring_rows + lane * R;
+        const bool notifier = lane == u.n_c / R - 1;       // wrote the boundary scores, so it publishes the progress
+        int slot = 0;
+        uint32_t spins = 0;
+        for (int cb = u.cb0; cb <= u.cbend; ++cb) {
+            while (seen_prev <= cb) {                       // the previous CTA's sweep has published block cb
+                seen_prev = ptx::ld_acquire_cluster_shared_a(done_prev_a);
+                if (seen_prev <= cb) __nanosleep(32);
+                if (++spins > kSpinLimit) systolic::spin_fail();
+            }
+            while (seen_next + kBndBlocks <= cb) {          // the next CTA's sweep has consumed block cb - ring depth
+                seen_next = ptx::ld_acquire_cluster_shared_a(done_next_a);
+                if (seen_next + kBndBlocks <= cb) __nanosleep(32);
+                if (++spins > kSpinLimit) systolic::spin_fail();
+            }
+            {   // this CTA's teams have stored the chunks the box spans
+                const int rel0 = (cb - u.cb0) * kBlk;
+                const int j0 = rel0 / u.F, j1 = min((rel0 + kBlk - 1) / u.F, u.nch - 1);
+                for (int j = j0; j <= j1; ++j) {
+                    const int team = j % g.nteams, need = j / g.nteams + 1;
+                    while (ld_acquire_shared(ctl + kTeamDone + team) < need) {
+                        __nanosleep(64);
+                        if (++spins > kSpinLimit) systolic::spin_fail();
+                    }
+                }
+            }
+            // score of token x0-1 at the last frame before this block -- when the previous CTA swept that
+            // block; if its slice starts in this very block, that cell is below the diagonal: -1e9 already
+            if (cb == u.cb0 && u.cb0 > ((u.x0 - u.n_c) >> 5) && u.x0 > 0)
+                carry = ptx::ld_shared_f32_a(bnd_a + (uint32_t)((((cb - 1) & (kBndBlocks - 1)) * kBlk + (kBlk - 1)) * 4));
+#pragma unroll
+            for (int i = 0; i < R; ++i) acc[i] = 0u;
+            const uint32_t tile_a = ring_a + (uint32_t)slot * box_bytes;
+            const uint32_t ring_slot = (uint32_t)(cb & (kBndBlocks - 1)) * (kBlk * 4);
+            const int col0 = cb * kBlk;
+            const bool on_diagonal = col0 <= x_last;        // warp-uniform: some token of the slice is below the diagonal here
+            if (on_diagonal) {
+                zero_below_diagonal_rows<R>(tile_a, lane, row0, col0, u.TR);
+                __syncwarp();
+            }
+            systolic::sweep_block<R, true>(tile_a, lane_c, v, acc, carry, bnd_a + ring_slot, bnd_out_base + ring_slot, publisher);
+#pragma unroll
+            for (int i = 0; i < R; ++i) acc[i] = __brev(acc[i]);
+            if (on_diagonal) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    // the forced step on the diagonal (frame == token, core.pyx:34), tokens > 0 only
+                    const int d = row0 + i - col0;
+                    if (d >= 0 && d < kBlk && row0 + i > 0) acc[i] |= 1u << d;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                if (lane * R + i < g.ring_rows) bits_p[i] = acc[i];
+            bits_p += g.ring_rows;
+            __syncwarp();                                   // every lane has read the box and the boundary slot
+            if (lane == 0) {
+                st_release_shared(ctl + kConsumed, cb - u.cb0 + 1);
+                zf.drip(zero_page, zf.per_block);
+            }
+            ptx::st_release_cluster_if(notifier && mirror_prev != 0u, mirror_prev, cb + 1);
+            ptx::st_release_cluster_if(notifier && mirror_next != 0u, mirror_next, cb + 1);
+            if (++slot == g.NB) slot = 0;
+        }
+        ptx::st_release_cluster_if(notifier && mirror_prev != 0u, mirror_prev, kDoneAll);
+        ptx::st_release_cluster_if(notifier && mirror_next != 0u, mirror_next, kDoneAll);
+        // a NaN or an infinity anywhere in a token's history is still in its score now
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+            if (lane * R + i < u.n_real && !(fabsf(v[i]) <= 3.402823466e38f)) nonfinite = 1;
+    }
+    if (kDbg && dbg && lane == 0) dbg[4] = ptx::globaltimer_ns();
+    if (lane == 0) {
+        zf.drip(zero_page, 0x7fffffff);
+        if (zf.total > 0) {
+            ptx::bulk_commit_group();
+            ptx::bulk_wait_all();                          // the ones are written after the next barriers
+        }
+    }
+    __syncwarp();
+    return nonfinite;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the literal redo of an utterance with non-finite scores (CTA 0 of the cluster, all its threads)
+// ---------------------------------------------------------------------------------------------
+static __device__ __forceinline__ void redo_utterance(const Geom &g, const Utt &u, const LogpParams &p, unsigned char *smem,
+                                                   float *scratch, uint32_t *bits, float neg) {
+    using namespace logp;
+    const TileShape &t = g.t_ref;
+    const int D = p.D, F = t.F, tx = u.tx, ty = u.ty;
+    float *sm = reinterpret_cast<float *>(smem + g.off_big);
+    const CtaSmem s = carve_smem(sm, D, t);
+    float *col = sm + cta_smem_floats(D, t);               // [2][tx], behind the contraction's operands
+    const systolic::Team team = systolic::whole_cta();
+    const systolic::ExactBits eb{0u, bits, u.n_c, g.nblk};
+    const int rts = ceil_div(tx, t.tile_rows);
+    const ChunkOut o{scratch, F, 0, true};
+    int buf = 0;
+    __syncthreads();                                        // the fast path's shared memory changes hands
+    systolic::exact_sweep_init(team, col, tx, neg);
+    for (int ch = 0; ch * F < ty; ++ch) {
+        for (int rt = 0; rt < rts; ++rt) {
+            if (rts > 1 || ch == 0) {
+                __syncthreads();
+                stage_tokens(p, s, t, u.b, rt * t.tile_rows);
+            }
+            if (rt == 0) {
+                stage_frames_async(p, s, t, u.b, ch, 0);
+                ptx::cp_async_wait<0>();
+                __syncthreads();
+                if (p.x_logs == nullptr) frame_sums_mean_only(s, D, F, 0);
+            }
+            contract_chunk(p, s, t, rt * t.tile_rows, ch, 0, 2, o);
+        }
+        __syncthreads();                                    // the chunk's scores are in the scratch (same CTA: visible)
+        systolic::exact_sweep_frames<true>(team, scratch - ch * F, F, col, buf, eb, tx, ch * F, min(ty, ch * F + F), neg);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int R, bool kDbg>
+__global__ void __launch_bounds__(kThreads, 1) mas_fused_kernel(PathParams pp, LogpParams lp, Geom g) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    // broadcast so that the compiler knows the warp index is warp-uniform (see dp_cta)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int K = g.K, c = (int)ptx::cluster_ctarank();
+    const int cluster_id = (int)blockIdx.x / K;
+    const int B = pp.B, T_x = pp.T_x, T_y = pp.T_y;
+    int *ctl = reinterpret_cast<int *>(smem + g.off_ctl);
+    volatile int *vctl = ctl;
+    float *bnd = reinterpret_cast<float *>(smem + g.off_bnd);
+    int2 *run = reinterpret_cast<int2 *>(smem + g.off_run);
+    uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem + g.off_bits);
+    const float neg = pp.max_neg_val;
+
+    // FFMA role: every warp but the sweep warp, or only those on the other three schedulers
+    // (a warp lives on scheduler warp % 4)
+    const bool is_ffma = warp != 0 && (g.ffma_all || (warp & 3) != 0);
+    const int fw = g.ffma_all ? warp - 1 : (warp - 1) - (warp >> 2);   // rank among the FFMA warps
+    const int fidx = fw * 32 + lane;
+    const int team = fw / g.team_warps, tn = g.team_warps * 32, ttid = fidx - team * tn;
+    const bool in_team = is_ffma && team < g.nteams;
+
+    {   // once per CTA: the zero page, and what "advances" into token 0 after frame 0 (core.pyx:26-27)
+        float4 *zero4 = reinterpret_cast<float4 *>(smem + g.off_zero);
+        for (int i = tid; i < kZeroPage / 16; i += kThreads) zero4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c == 0)
+            for (int i = tid; i < kBndBlocks * kBlk; i += kThreads) bnd[i] = neg;
+        ptx::fence_proxy_async();
+        __syncthreads();
+    }
+    long long *dbg = (kDbg && pp.dbg_cycles) ? pp.dbg_cycles + (size_t)blockIdx.x * 16 : nullptr;
+
+    for (int it = 0;; ++it) {
+        // static, serpentine: batches come sorted by length (dataset.py:79-81), so consecutive rounds
+        // in alternating directions even out the clusters' totals
+        const int b = it * g.NC + ((it & 1) ? g.NC - 1 - cluster_id : cluster_id);
+        if (b >= B) break;
+        Utt u;
+        u.b = b;
+        u.c = c;
+        {
+            const Lengths len = clamp_lengths(lp.x_len[b], lp.y_len[b], T_x, T_y);
+            u.tx = len.tx;
+            u.ty = len.ty;
+        }
+        u.n_c = max(R, ceil_div(ceil_div(u.tx, K), R) * R);
+        u.x0 = c * u.n_c;
+        u.n_real = max(0, min(u.n_c, u.tx - u.x0));
+        u.TR = ceil_div(u.n_c, kGemmTM) * kGemmTM;
+        u.RG = u.TR / kGemmTM;
+        u.CG = max(1, min(tn / u.RG, g.CG_cap));
+        u.F = 8 * u.CG;
+        u.cb0 = u.x0 >> 5;
+        u.cbend = u.n_real > 0 ? min(u.ty - 1, u.x0 + u.n_real - 1 + (u.ty - u.tx)) >> 5 : u.cb0 - 1;
+        u.nch = ceil_div((u.cbend - u.cb0 + 1) * kBlk, u.F);
+        const bool active = u.n_real > 0;
+
+        if (tid == 0) {
+            for (int i = 0; i < kMaxTeams; ++i) ctl[kTeamDone + i] = 0;
+            ctl[kConsumed] = 0;
+            ctl[kDonePrev] = (c == 0) ? kDoneAll : -1;
+            if (c == K - 1) ctl[kDoneNext] = kDoneAll;
+            ctl[kBtFlag] = 0;
+            ctl[kRedo] = 0;
+            if (c > 0)   // tell the previous CTA where its consumer (this sweep) starts
+                ptx::st_cluster_u32(ptx::mapa(ptx::smem_u32(ctl + kDoneNext), (uint32_t)(c - 1)), (uint32_t)(active ? u.cb0 - 1 : kDoneAll));
+        }
+        if (kDbg && dbg && tid == 0) dbg[0] = ptx::globaltimer_ns();
+        ptx::cluster_sync();
+
+        int nonfinite = 0;
+        if (warp == 0) {
+            ZeroFill zf;
+            const int rs = ceil_div(T_x, K), r0 = min(T_x, c * rs), r1 = min(T_x, r0 + rs);
+            zf.dst = reinterpret_cast<char *>(pp.path + ((int64_t)b * T_x + r0) * T_y);
+            zf.total = (int64_t)(r1 - r0) * T_y * 4;        // multiple of 16: T_y % 4 == 0 on this path
+            zf.off = 0;
+            zf.per_block = ceil_div((int)((zf.total + kZeroPage - 1) / kZeroPage), max(1, u.cbend - u.cb0 + 1));
+            uint32_t *bits_g = g.bits_in_smem ? nullptr : g.ws_bits + ((size_t)cluster_id * K + c) * g.nblk * g.ring_rows;
+            nonfinite = sweep_slice<R, kDbg>(g, u, smem, ctl, neg, zf, bits_g, dbg);
+        } else if (in_team && active) {
+            stage_ops(g, u, lp, smem, fidx, g.nteams * tn);
+            if (kDbg && dbg && fidx == 0) dbg[1] = ptx::globaltimer_ns();
+            if (lp.x_logs == nullptr)
+                team_contract<true>(g, u, lp, smem, ctl, team, ttid, tn);
+            else
+                team_contract<false>(g, u, lp, smem, ctl, team, ttid, tn);
+            if (kDbg && dbg && ttid == 0) dbg[8 + team] = ptx::globaltimer_ns();
+        }
+        if (!g.bits_in_smem) __threadfence();
+
+        // ---- were all scores finite?  (cluster-wide) ----
+        const int any_bad = __syncthreads_or(nonfinite);
+        if (any_bad && tid == 0)
+            for (int r = 0; r < K; ++r) ptx::st_cluster_u32(ptx::mapa(ptx::smem_u32(ctl + kRedo), (uint32_t)r), 1u);
+        ptx::cluster_sync();
+        const bool redo = vctl[kRedo] != 0;
+        const uint32_t *bits_gl = g.bits_in_smem ? nullptr : g.ws_bits + ((size_t)cluster_id * K + c) * g.nblk * g.ring_rows;
+        int bits_rows = g.ring_rows;
+        if (redo) {
+            uint32_t *rb = g.redo_bits + (size_t)cluster_id * g.nblk * (T_x + 64);
+            if (c == 0) {
+                redo_utterance(g, u, lp, smem, g.redo_scratch + (size_t)cluster_id * T_x * g.t_ref.F, rb, neg);
+                __threadfence();
+            }
+            ptx::cluster_sync();
+            bits_gl = rb + (size_t)c * g.nblk * u.n_c;
+            bits_rows = u.n_c;
+        }
+        if (kDbg && dbg && tid == 0) dbg[5] = ptx::globaltimer_ns();
+
+        // ---- backtrack (core.pyx:32-35) by TOKENS, handed down from CTA to CTA ----
+        const int c_last = (u.tx > 0) ? (u.tx - 1) / u.n_c : -1;   // CTA that owns the last token
+        if (tid == 0 && c <= c_last) {
+            int x, y_hi;
+            if (c == c_last) {
+                x = u.tx - 1;
+                y_hi = u.ty - 1;
+            } else {
+                uint32_t spins = 0;
+                while (ptx::ld_acquire_cluster_shared(ctl + kBtFlag) == 0)
+                    if (++spins > kSpinLimit) systolic::spin_fail();
+                x = vctl[kBtToken];
+                y_hi = vctl[kBtFrame];
+            }
+            const int x_min = max(u.x0, 1);
+            if (x >= x_min)
+                y_hi = (bits_gl == nullptr) ? systolic::backtrack_tokens<true>(bits_s, bits_rows, u.x0, x, y_hi, x_min, run)
+                                            : systolic::backtrack_tokens<false>(bits_gl, bits_rows, u.x0, x, y_hi, x_min, run);
+            if (c == 0) {
+                run[0] = make_int2(0, y_hi);
+            } else {
+                const uint32_t peer = ptx::mapa(ptx::smem_u32(ctl + kBtFlag), (uint32_t)(c - 1));
+                ptx::st_cluster_u32(peer + 4, (uint32_t)(u.x0 - 1));
+                ptx::st_cluster_u32(peer + 8, (uint32_t)y_hi);
+                ptx::st_release_cluster_if(true, peer, 1);
+            }
+        }
+        __syncthreads();
+        if (kDbg && dbg && tid == 0) dbg[6] = ptx::globaltimer_ns();
+
+        // ---- dense path: ones, durations, frame -> token ----
+        float *out = pp.path + (int64_t)b * T_x * T_y;
+        for (int xl = tid; xl < u.n_real; xl += kThreads) {
+            const int x = u.x0 + xl;
+            const int2 r = run[xl];
+            float *row = out + (int64_t)x * T_y;
+            for (int y = r.x; y <= r.y; ++y) row[y] = 1.f;
+            if (pp.frame_token)
+                for (int y = r.x; y <= r.y; ++y) pp.frame_token[(int64_t)b * T_y + y] = x;
+            if (pp.durations) pp.durations[(int64_t)b * T_x + x] = r.y - r.x + 1;
+        }
+        if (pp.durations)
+            for (int x = u.tx + c * kThreads + tid; x < T_x; x += K * kThreads) pp.durations[(int64_t)b * T_x + x] = 0;
+        if (pp.frame_token && c == 0)
+            for (int y = u.ty + tid; y < T_y; y += kThreads) pp.frame_token[(int64_t)b * T_y + y] = -1;
+        if (kDbg && dbg && tid == 0) dbg[7] = ptx::globaltimer_ns();
+        // nobody may reset its control words (next utterance) or leave while a neighbour can still write them
+        ptx::cluster_sync();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int tokens_per_lane(int T_x, int K) {
+    int R = ceil_div(ceil_div(T_x, K), kBlk);
+    if (R < 1) R = 1;
+    if (R == 7) R = 8;
+    return R;
+}
+
+// Shared-memory layout and team shape for K CTAs per utterance; false when it does not fit.
+static bool make_geom(int D, int T_x, int T_y, int K, int ffma_all, int teams_forced, int max_smem, Geom &g) {
+    g = Geom{};
+    const int R = tokens_per_lane(T_x, K);
+    if (R > 8) return false;
+    g.K = K;
+    g.ffma_all = ffma_all;
+    g.max_slice = ceil_div(ceil_div(T_x, K), R) * R;
+    g.tr_max = ceil_div(g.max_slice, kGemmTM) * kGemmTM;
+    g.ring_rows = ceil_div(g.tr_max, 8) * 8;
+    g.nblk = ceil_div(T_y, kBlk);
+    g.t_ref = make_tile_shape(T_x, T_y);
+    g.nsh = kGemmThreads / g.t_ref.tile_rows;
+    g.nsh = g.nsh < 1 ? 1 : (g.nsh > 4 ? 4 : g.nsh);
+    g.dsh = ceil_div(D, g.nsh);
+    const int RG = g.tr_max / kGemmTM, warps = ffma_all ? 15 : 12;
+    // teams: as many as keep the threads busy (finer chunks: the sweep starts earlier and trails less)
+    double best = -1.0;
+    for (int nt = 1; nt <= 5; ++nt) {
+        if (warps % nt) continue;
+        if (teams_forced > 0 && nt != teams_forced) continue;
+        const int tw = warps / nt, tn = tw * 32;
+        int cg = tn / RG;
+        cg = cg > 32 ? 32 : cg;
+        cg = cg > tn / 8 ? tn / 8 : cg;
+        if (cg < 4) continue;
+        const double score = (double)(RG * cg * nt) / (warps * 32) * (1.0 + 0.02 * nt);
+        if (score > best) {
+            best = score;
+            g.nteams = nt;
+            g.team_warps = tw;
+            g.CG_cap = cg;
+        }
+    }
+    if (best < 0) return false;
+    g.F_cap = 8 * g.CG_cap;
+
+    int off = 0;
+    g.off_zero = off, off += kZeroPage;
+    g.off_bnd = off, off += kBndBlocks * kBlk * 4;
+    g.off_run = off, off += g.ring_rows * 8;
+    g.off_ctl = off, off += kCtlInts * 4;
+    off = (int)align_up((size_t)off, 1024);
+    g.off_big = off;
+    g.off_ops = off, off += 2 * D * g.tr_max * 4;
+    g.off_l14 = off, off += 2 * g.tr_max * 4;
+    g.off_part = off, off += 8 * g.tr_max * 4;
+    g.off_z = off, off += g.nteams * 2 * kChan * g.F_cap * 4;
+    g.off_l2 = off, off += g.nteams * g.F_cap * 4;
+    off = (int)align_up((size_t)off, 1024);
+    g.off_ring = off;
+    const int box = g.ring_rows * 128;
+    const int nb_min = ceil_div((g.nteams + 1) * g.F_cap + kBlk, kBlk);
+    const int bits_bytes = g.nblk * g.ring_rows * 4;
+    const int redo_need = g.off_big + logp::cta_smem_floats(D, g.t_ref) * 4 + 2 * T_x * 4 + 16;
+    if (redo_need > max_smem) return false;
+    for (int bits_smem = 1; bits_smem >= 0; --bits_smem) {
+        const int left = max_smem - g.off_ring - (bits_smem ? bits_bytes : 0);
+        int nb = left / box;
+        if (nb > 32) nb = 32;
+        if (nb >= nb_min) {
+            g.NB = nb;
+            g.bits_in_smem = bits_smem;
+            g.off_bits = g.off_ring + nb * box;
+            g.total = g.off_bits + (bits_smem ? bits_bytes : 0);
+            if (g.total < redo_need) g.total = redo_need;
+            return true;
+        }
+    }
+    return false;
+}
+
+static size_t redo_scratch_bytes(int slots, int T_x, int T_y) {
+    const TileShape t = make_tile_shape(T_x, T_y);
+    return align_up((size_t)slots * T_x * t.F * 4, 256);
+}
+static size_t redo_bits_bytes(int slots, int T_x, int T_y) { return align_up((size_t)slots * ceil_div(T_y, kBlk) * (T_x + 64) * 4, 256); }
+static size_t ws_bits_bytes(int slots, int T_x, int T_y) {
+    // [clusters][K][nblk][ring_rows]: K x ring_rows <= T_x + K x (R + 4 + 8) rounding
+    return align_up((size_t)slots * ceil_div(T_y, kBlk) * (T_x + 160) * 4, 256);
+}
+
 template <int R>
-static int launch_r(const CUtensorMap &tmap, const PathParams &pp, const systolic::Plan &plan, const LogpParams &lp,
-                    const Geometry &g, int smem_bytes, cudaStream_t stream) {
-    static int configured[64] = {0};
-    int dev = 0;
-    MAS_CUDA_TRY(cudaGetDevice(&dev));
-    if (pp.dbg_cycles != nullptr) {
-        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        mas_fused_kernel<R, true><<<g.P + (pp.B + g.teams - 1) / g.teams, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
-        MAS_CUDA_TRY(cudaGetLastError());
-        return MAS_OK;
+static int launch_r(const PathParams &pp, const LogpParams &lp, Geom &g, int B, int dev, cudaStream_t stream) {
+    static SmemOptIn optin[2];
+    const bool dbgk = pp.dbg_cycles != nullptr;
+    auto kern = dbgk ? mas_fused_kernel<R, true> : mas_fused_kernel<R, false>;
+    if (int rc = optin[dbgk].ensure(kern, dev, g.total)) return rc;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)g.total;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)g.K;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // how many clusters the device holds at once (per device and K: the query is not free)
+    static std::atomic<int> cache[2][64][9];
+    int nc = cache[dbgk][dev & 63][g.K].load();
+    if (nc == 0) {
+        cfg.gridDim = dim3((unsigned)(g.K * kMaxClusters));
+        MAS_CUDA_TRY(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
+        if (nc < 1) return MAS_ERR_UNSUPPORTED_SHAPE;
+        cache[dbgk][dev & 63][g.K].store(nc);
     }
-    if (smem_bytes > configured[dev & 63]) {
-        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        configured[dev & 63] = smem_bytes;
-    }
-    if (getenv("MAS_B200_DEBUG") != nullptr) {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mas_fused_kernel<R, false>, kThreads, smem_bytes);
-        cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, mas_fused_kernel<R, false>);
-        fprintf(stderr, "[mas_b200] fused kernel: %d CTAs/SM resident, %d regs, %zu B static smem\n", nb, fa.numRegs, fa.sharedSizeBytes);
-    }
-    mas_fused_kernel<R, false><<<g.P + (pp.B + g.teams - 1) / g.teams, kThreads, smem_bytes, stream>>>(tmap, pp, plan, lp, g);
-    MAS_CUDA_TRY(cudaGetLastError());
+    if (nc > kMaxClusters) nc = kMaxClusters;
+    g.NC = B < nc ? B : nc;
+    cfg.gridDim = dim3((unsigned)(g.NC * g.K));
+    MAS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, pp, lp, g));
     return MAS_OK;
+}
+
+// The geometry for `num_sms` SMs with `max_smem` bytes of opt-in shared memory per CTA.
+static bool choose_geom(int B, int D, int T_x, int T_y, int max_smem, int num_sms, Geom &best) {
+    static const char *k_env = getenv("MAS_B200_FUSED_K");          // experiment hooks
+    static const char *ffma_env = getenv("MAS_B200_FUSED_FFMA");
+    static const char *teams_env = getenv("MAS_B200_FUSED_TEAMS");
+    const int ffma_all = ffma_env ? (atoi(ffma_env) >= 15) : 1;
+    const int teams_forced = teams_env ? atoi(teams_env) : 0;
+    double best_cost = -1.0;
+    for (int K = 1; K <= 8; K *= 2) {
+        if (k_env && atoi(k_env) != K) continue;
+        if (K > 1 && ceil_div(T_x, K) < 8) continue;                // slices of a handful of tokens are not worth a CTA
+        Geom g;
+        if (!make_geom(D, T_x, T_y, K, ffma_all, teams_forced, max_smem, g)) continue;
+        const int nc = num_sms / K;
+        if (nc < 1) continue;
+        const int rounds = ceil_div(B, nc);
+        const double cost = rounds * (1.0 / K + 0.04);              // a slice's share of the work + what a cluster costs
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = g;
+        }
+    }
+    return best_cost >= 0;
 }
 
 }  // namespace fused
 
-static size_t fused_flag_bytes(int B, int T_y) {      // ready counters, one per chunk (chunks are >= 64 frames)
-    return align_up((size_t)B * (ceil_div(T_y, 8 * kGemmMinCG) + 1) * 4, 256);
-}
-
+// Scratch of the single launch: per resident cluster (at most 192) the redo scratch and direction
+// bits; no score matrix, no rings.  Independent of the batch size beyond 192 utterances.
 size_t fused_workspace_bytes(int B, int D, int T_x, int T_y) {
     (void)D;
-    return align_up((size_t)B * T_x * T_y * 4, 256) + fused_flag_bytes(B, T_y) + path_systolic_workspace_bytes(B, T_x, T_y);
+    using namespace fused;
+    const int slots = B < kMaxClusters ? B : kMaxClusters;
+    return redo_scratch_bytes(slots, T_x, T_y) + redo_bits_bytes(slots, T_x, T_y) + ws_bits_bytes(slots, T_x, T_y);
 }
 
-// MAS_OK: launched.  MAS_ERR_UNSUPPORTED_SHAPE: not for the single-launch path (the caller runs the two
+// Host-only: the geometry the launcher picks.
+// out12 = {K, R, max_slice, nteams, team_warps, CG, F, NB, bits_in_smem, total, ffma warps, ring_rows}.
+bool debug_fused_geom(int B, int D, int T_x, int T_y, int max_smem, int num_sms, int32_t *out12) {
+    fused::Geom g;
+    if (!fused::choose_geom(B, D, T_x, T_y, max_smem, num_sms, g)) return false;
+    out12[0] = g.K, out12[1] = fused::tokens_per_lane(T_x, g.K), out12[2] = g.max_slice, out12[3] = g.nteams;
+    out12[4] = g.team_warps, out12[5] = g.CG_cap, out12[6] = g.F_cap, out12[7] = g.NB, out12[8] = g.bits_in_smem;
+    out12[9] = g.total, out12[10] = g.ffma_all ? 15 : 12, out12[11] = g.ring_rows;
+    return true;
+}
+
+// MAS_OK: launched.  MAS_ERR_UNSUPPORTED_SHAPE: not for the single launch (the caller runs the two
 // kernels back to back instead).
 int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y_len, float *path, int32_t *durations,
                  int32_t *frame_token, void *workspace, size_t workspace_bytes, float max_neg_val, cudaStream_t stream) {
@@ -123,139 +805,54 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
 #define MAS_FUSED_NO(why) do { if (debug) fprintf(stderr, "[mas_b200] single launch not taken: %s\n", why); return MAS_ERR_UNSUPPORTED_SHAPE; } while (0)
     const int B = lp_in.B, D = lp_in.D, T_x = lp_in.T_x, T_y = lp_in.T_y;
     if (B == 0) return MAS_OK;
-    if ((T_y & 3) || T_y < systolic::kBlk || D > logp::kPanel || D < 1 ||
-        (reinterpret_cast<uintptr_t>(lp_in.z) & 15) || (reinterpret_cast<uintptr_t>(path) & 15))
+    if ((T_y & 3) || D > logp::kPanel || D < 1 || (reinterpret_cast<uintptr_t>(lp_in.z) & 15) ||
+        (reinterpret_cast<uintptr_t>(path) & 15))
         MAS_FUSED_NO("alignment / frame count / channel count");
-    int R, W;
-    if (!systolic::choose_shape(T_x, R, W) || (W + 1) * 32 > kThreads) MAS_FUSED_NO("too many sweep warps");
-    PFN_cuTensorMapEncodeTiled_v12000 encode = systolic::get_encode_fn();
-    if (encode == nullptr) MAS_FUSED_NO("no cuTensorMapEncodeTiled");
     if (workspace == nullptr || workspace_bytes < fused_workspace_bytes(B, D, T_x, T_y)) return MAS_ERR_WORKSPACE_TOO_SMALL;
 
-    static int max_smem_cached[64] = {0}, num_sms_cached[64] = {0};
     int dev = 0;
     MAS_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return MAS_ERR_INVALID_ARGUMENT;
-    if (max_smem_cached[dev] == 0) {
-        MAS_CUDA_TRY(cudaDeviceGetAttribute(&max_smem_cached[dev], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        MAS_CUDA_TRY(cudaDeviceGetAttribute(&num_sms_cached[dev], cudaDevAttrMultiProcessorCount, dev));
-    }
-    const int max_smem = max_smem_cached[dev] - 2048;
-    const int num_sms = num_sms_cached[dev];
+    DeviceInfo di{};
+    if (int rc = get_device_info(dev, di)) return rc;
+    Geom g;
+    if (!choose_geom(B, D, T_x, T_y, di.max_smem_optin - 1024, di.num_sms, g)) MAS_FUSED_NO("no slice geometry fits shared memory");
 
-    Geometry g{};
-    g.t = make_tile_shape(T_x, T_y);
-    const int BT = B * g.t.row_tiles;
-    const int gemm_smem = logp::cta_smem_floats(D, g.t) * 4;
-    if (gemm_smem > max_smem) MAS_FUSED_NO("shared memory (producers)");
-
-    // sweep CTAs (K = 1): one utterance per CTA with the deepest ring that fits.
-    // Experiment hook MAS_B200_FUSED_TWO_TEAMS: two utterances per sweep CTA (a half CTA -- 8 warps --
-    // and half the shared memory each), so that the sweeps hold B/2 SMs and the producers get 16
-    // more.  Measured at C2: the producers then finish at 58 us instead of 69, but the sweeps -- two
-    // per scheduler, ring only two boxes deep -- take 55 us instead of 42 and become the critical
-    // path: 110 us per step against 94.  Off by default.
-    static const bool two_teams = getenv("MAS_B200_FUSED_TWO_TEAMS") != nullptr;
-    systolic::Plan plan{};
-    bool ok = false;
-    g.teams = 1;
-    if (two_teams && B > 1) {
-        const int groups = ceil_div(T_x, systolic::kBlk);
-        for (int r : {R, 2, 3, 5, 4, 6, 8}) {
-            const int w = ceil_div(groups, r);
-            if (w + 1 > kThreads / 64) continue;                      // 8 warps per team
-            for (int S = 4; S >= 2 && !ok; --S) {
-                systolic::Plan pl = systolic::make_plan(r, w, S, 1, T_y, true, 8192);
-                const int stride = (int)align_up((size_t)pl.total, 1024);
-                if (2 * stride <= max_smem) {
-                    plan = pl;
-                    g.teams = 2;
-                    g.team_stride = stride;
-                    ok = true;
-                }
-            }
-            if (ok) break;
-        }
-    }
-    for (int bits_smem = 1; bits_smem >= 0 && !ok; --bits_smem)
-        for (int S = 4; S >= 2 && !ok; --S) {
-            plan = systolic::make_plan(R, W, S, 1, T_y, bits_smem != 0, 8192);
-            ok = plan.total <= max_smem;
-        }
-    if (!ok) MAS_FUSED_NO("shared memory (sweep)");
-    const int sweep_smem = g.teams == 2 ? 2 * g.team_stride : plan.total;
-    int smem_bytes = gemm_smem > sweep_smem ? gemm_smem : sweep_smem;
-    const int solo = (max_smem_cached[dev] + 1024) / 2;                 // more than half an SM: one CTA per SM
-    if (smem_bytes < solo) smem_bytes = solo;
-
-    // the SMs the sweeps do not hold produce; with fewer than two producers per token tile they
-    // would be the long pole and two full-width launches are faster
-    g.P = num_sms - ceil_div(B, g.teams);
-    if (g.P < 2 * BT) MAS_FUSED_NO("too many utterances for one wave");
-    // Experiment hook MAS_B200_FUSED_HEAD=n: the sweep CTA of an utterance contracts its first n
-    // chunks itself (its SM idles until the first scores exist) and the producers' deal covers the
-    // rest.  Measured at C2 (graph of 10 steps): n = 0 / 1 / 2 / 3 -> 99 / 109 / 120 / 137 us per step.
-    // A head chunk costs the sweep CTA a full unit although most of its cells are below the diagonal
-    // (17-20 us: the sweep starts at 27 / 44 us instead of 24), the sweep itself needs 55-60 us after
-    // its start, and 12 or 11 chunks over three producers are still four rounds.  Off by default.
-    g.head = 0;
-    if (g.teams == 1) {
-        static const char *head_env = getenv("MAS_B200_FUSED_HEAD");
-        g.head = head_env ? atoi(head_env) : 0;
-        const int cap = g.t.nchunks / 4;                // the sweep still has most of the utterance to wait for
-        if (g.head > cap) g.head = cap;
-        if (g.head < 0) g.head = 0;
-    }
-    g.deal = logp::make_deal(g.P, BT, g.t.nchunks - g.head);
-
+    const int slots = B < kMaxClusters ? B : kMaxClusters;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    float *scores = reinterpret_cast<float *>(ws);
-    ws += align_up((size_t)B * T_x * T_y * 4, 256);
-    g.ready = reinterpret_cast<int *>(ws);
-    ws += fused_flag_bytes(B, T_y);
-    MAS_CUDA_TRY(cudaMemsetAsync(g.ready, 0, (size_t)B * g.t.nchunks * 4, stream));
+    g.redo_scratch = reinterpret_cast<float *>(ws);
+    ws += redo_scratch_bytes(slots, T_x, T_y);
+    g.redo_bits = reinterpret_cast<uint32_t *>(ws);
+    ws += redo_bits_bytes(slots, T_x, T_y);
+    g.ws_bits = reinterpret_cast<uint32_t *>(ws);
 
     LogpParams lp = lp_in;
-    lp.logp = scores;
+    lp.logp = nullptr;
     lp.x_len = x_len;
     lp.y_len = y_len;
     PathParams pp{};
-    pp.value = scores;
-    pp.value_stride_b = (int64_t)T_x * T_y;
-    pp.value_stride_x = T_y;
     pp.t_x = x_len;
     pp.t_y = y_len;
     pp.path = path;
     pp.durations = durations;
     pp.frame_token = frame_token;
-    pp.ws_bits = plan.bits_in_smem ? nullptr : reinterpret_cast<uint32_t *>(ws);
     pp.B = B;
     pp.T_x = T_x;
     pp.T_y = T_y;
     pp.max_neg_val = max_neg_val;
     pp.dbg_cycles = g_dbg_cycles.load();
 
-    CUtensorMap tmap;
-    const cuuint64_t gdim[3] = {(cuuint64_t)T_y, (cuuint64_t)T_x, (cuuint64_t)B};
-    const cuuint64_t gstride[2] = {(cuuint64_t)T_y * 4, (cuuint64_t)T_x * T_y * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)systolic::kBlk, (cuuint32_t)(systolic::kBlk * plan.R), 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, scores, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) MAS_FUSED_NO("tensor map encode failed");
+    const int R = tokens_per_lane(T_x, g.K);
     if (debug)
-        fprintf(stderr, "[mas_b200] single launch: %d producers (%d per tile + %d spares, cover %d of %d chunks of %d frames after %d head chunks, tiles of %d tokens) + %d sweep CTAs of %d utterance(s), %d B smem, R=%d W=%d S=%d\n",
-                g.P, g.deal.d, g.deal.spares, g.deal.cover, g.deal.nchunks, g.t.F, g.head, g.t.tile_rows, ceil_div(B, g.teams), g.teams, smem_bytes,
-                plan.R, plan.W, plan.S);
-
-    switch (plan.R) {
-        case 1: return launch_r<1>(tmap, pp, plan, lp, g, smem_bytes, stream);
-        case 2: return launch_r<2>(tmap, pp, plan, lp, g, smem_bytes, stream);
-        case 3: return launch_r<3>(tmap, pp, plan, lp, g, smem_bytes, stream);
-        case 4: return launch_r<4>(tmap, pp, plan, lp, g, smem_bytes, stream);
-        case 5: return launch_r<5>(tmap, pp, plan, lp, g, smem_bytes, stream);
-        case 6: return launch_r<6>(tmap, pp, plan, lp, g, smem_bytes, stream);
-        case 8: return launch_r<8>(tmap, pp, plan, lp, g, smem_bytes, stream);
+        fprintf(stderr, "[mas_b200] single launch: clusters of %d CTAs, slices of <= %d tokens (R=%d), %d FFMA warps in %d teams, chunks of <= %d frames, ring of %d boxes x %d rows, bits %s, %d B smem\n",
+                g.K, g.max_slice, R, g.ffma_all ? 15 : 12, g.nteams, g.F_cap, g.NB, g.ring_rows, g.bits_in_smem ? "in smem" : "in workspace", g.total);
+    switch (R) {
+        case 1: return launch_r<1>(pp, lp, g, B, dev, stream);
+        case 2: return launch_r<2>(pp, lp, g, B, dev, stream);
+        case 3: return launch_r<3>(pp, lp, g, B, dev, stream);
+        case 4: return launch_r<4>(pp, lp, g, B, dev, stream);
+        case 5: return launch_r<5>(pp, lp, g, B, dev, stream);
+        case 6: return launch_r<6>(pp, lp, g, B, dev, stream);
+        case 8: return launch_r<8>(pp, lp, g, B, dev, stream);
         default: return MAS_ERR_UNSUPPORTED_SHAPE;
     }
 }

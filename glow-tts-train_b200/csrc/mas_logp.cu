@@ -26,7 +26,7 @@ struct Geometry {
 __global__ void __launch_bounds__(kGemmThreads, 1) mas_logp_kernel(LogpParams p, Geometry g) {
     extern __shared__ __align__(16) float sm[];
     if (!g.generic) {
-        run_deal<false>(p, sm, g.t, g.deal, blockIdx.x, nullptr, 0);
+        run_deal(p, sm, g.t, g.deal, blockIdx.x);
         return;
     }
     // ---- generic path: any alignment, any channel count (panels of 80); one (row, chunk) unit at a time ----

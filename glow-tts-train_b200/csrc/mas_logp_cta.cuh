@@ -21,75 +21,55 @@ __host__ __device__ inline int cta_smem_floats(int D, const TileShape &t) {
     return 2 * D * t.tile_rows + 2 * D * t.F + 2 * t.tile_rows + t.F + 8 * t.tile_rows;
 }
 
-// chunks chunk_first, chunk_first + chunk_stride, ... (chunk_count of them) of token tile x0 of
-// utterance b; indices from skip_from up are shifted by skip_by (the chunks the spare CTAs take);
-// the whole numbering starts at chunk `chunk_base` of the utterance (single launch: the chunks
-// before it are produced by the utterance's own sweep CTA, mas_fused.cu)
-template <bool kSignal>
-__device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, const TileShape &t, int b, int x0, int chunk_first,
-                                         int chunk_stride, int chunk_count, int skip_from, int skip_by, int chunk_base,
-                                         int *ready, long long *dbg_ns = nullptr) {
-    if (chunk_count <= 0) return;
-    const int D = p.D, T_x = p.T_x, T_y = p.T_y;
-    const int tile_rows = t.tile_rows, F = t.F, CG = t.CG;
-    float *sInv = sm;                                   // [D][tile_rows]
-    float *sMiv = sInv + D * tile_rows;                 // [D][tile_rows]
-    float *sZ = sMiv + D * tile_rows;                   // [2][D][F]  (double-buffered chunk of z)
-    float *sL1 = sZ + 2 * D * F;                        // [tile_rows]
-    float *sL4 = sL1 + tile_rows;                       // [tile_rows]
-    float *sL2 = sL4 + tile_rows;                       // [F] mean_only: per-frame sum of -0.5 z^2
-    const bool mean_only = p.x_logs == nullptr;         // config.py:52, the reference default
+// ---------------------------------------------------------------------------------------------
+// The three steps of one (utterance, token tile, chunk) unit, shared by every kernel that contracts
+// scores: the materialising kernel walks them over a static list of chunks (logp_cta below), the
+// single launch (mas_fused.cu) over units it claims at run time.  Same operands, same order of
+// operations everywhere -> bit-identical scores.
+// ---------------------------------------------------------------------------------------------
+struct CtaSmem {
+    float *sInv, *sMiv, *sZ, *sL1, *sL4, *sL2, *sPart;
+};
+__device__ __forceinline__ CtaSmem carve_smem(float *sm, int D, const TileShape &t) {
+    CtaSmem s;
+    s.sInv = sm;                                    // [D][tile_rows]
+    s.sMiv = s.sInv + D * t.tile_rows;              // [D][tile_rows]
+    s.sZ = s.sMiv + D * t.tile_rows;                // [2][D][F]  (double-buffered chunk of z)
+    s.sL1 = s.sZ + 2 * D * t.F;                     // [tile_rows]
+    s.sL4 = s.sL1 + t.tile_rows;                    // [tile_rows]
+    s.sL2 = s.sL4 + t.tile_rows;                    // [F] mean_only: per-frame sum of -0.5 z^2
+    s.sPart = s.sL2 + t.F;                          // [nsh <= 4][2][tile_rows] partial row constants
+    return s;
+}
 
+// frames [ch F, ch F + F) of z, all channels, into buffer `buf` (cp.async, 16-byte pieces; frames
+// beyond T_y are zero-filled).  Commits one cp.async group.
+__device__ __forceinline__ void stage_frames_async(const LogpParams &p, const CtaSmem &s, const TileShape &t, int b, int ch,
+                                                   int buf) {
+    const int D = p.D, T_y = p.T_y, F = t.F, f4 = F >> 2;
+    const float *zg = p.z + (int64_t)b * D * T_y;
+    const int y0 = ch * F;
+    float *dst = s.sZ + buf * D * F;
+    for (int i = threadIdx.x; i < D * f4; i += blockDim.x) {
+        const int d = i / f4, y = y0 + ((i - d * f4) << 2);
+        ptx::cp_async_16(dst + (i << 2), zg + (int64_t)d * T_y + (y < T_y ? y : 0), y < T_y);
+    }
+    ptx::cp_async_commit();
+}
+
+// token side of tile [x0, x0 + tile_rows) of utterance b: thread (x, h) stages token x0+x for one
+// contiguous share of the channels (coalesced over x) and sums its share of the row constants,
+// channels ascending; the shares are then added in order.  nsh = how many threads serve a token
+// (2 at 512 / 200).  The loop is kept SMALL: this is cold code that every warp runs once, and
+// unrolled by 20 it was bound by instruction fetch (stall_no_inst, profiles/r1_ncu_logp.txt), not
+// by the loads.  Ends with a CTA barrier; the caller guarantees nobody still reads the old tile.
+__device__ __forceinline__ void stage_tokens(const LogpParams &p, const CtaSmem &s, const TileShape &t, int b, int x0) {
+    const int D = p.D, T_x = p.T_x, tile_rows = t.tile_rows;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const float *xm = p.x_m + (int64_t)b * D * T_x;
     const float *xl = p.x_logs ? p.x_logs + (int64_t)b * D * T_x : nullptr;
-    const float *zg = p.z + (int64_t)b * D * T_y;
-    float *out = p.logp + (int64_t)b * T_x * T_y;
-    const int rg = tid / CG, cg = tid - rg * CG;        // 4 tokens x {4+4} frames per thread
-    const bool worker = rg < t.RG;
-    // Single launch: only the sweep reads these scores, and only inside the reference's band
-    // (core.pyx:18: max(0, t_x + y - t_y) <= x < min(t_x, y + 1)).  A thread whose four tokens are
-    // outside the band for every frame of the chunk skips the contraction and stores zeros (the
-    // sweep's boxes still cover those cells: they must be finite, their value is irrelevant);
-    // tokens beyond t_x and chunks more than a box past t_y are not touched at all.  With full
-    // lengths (200 x 1000) that is 15 % of the cells, with ragged batches whatever the padding is.
-    const bool banded = kSignal && p.x_len != nullptr;
-    int band_tx = T_x, band_ty = T_y;
-    if (banded) {
-        const Lengths len = clamp_lengths(p.x_len[b], p.y_len[b], T_x, T_y);
-        band_tx = len.tx;
-        band_ty = len.ty;
-    }
-    const int f4 = F >> 2;                              // 16-byte pieces per chunk row
-
-    auto stage_frames_async = [&](int ch, int buf) {
-        const int y0 = ch * F;
-        float *dst = sZ + buf * D * F;
-        for (int i = tid; i < D * f4; i += nthr) {
-            const int d = i / f4, y = y0 + ((i - d * f4) << 2);
-            ptx::cp_async_16(dst + (i << 2), zg + (int64_t)d * T_y + (y < T_y ? y : 0), y < T_y);
-        }
-        ptx::cp_async_commit();
-    };
-
-    // the sequence is kept in un-shifted numbering; `ch` is the real chunk
-    int seq = chunk_first;
-    auto next_chunk = [&](int) {
-        seq += chunk_stride;
-        return (seq >= skip_from ? seq + skip_by : seq) + chunk_base;
-    };
-    __syncthreads();                                    // a previous tile of this CTA is done with the shared memory
-    int ch = (seq >= skip_from ? seq + skip_by : seq) + chunk_base;
-    if (dbg_ns && tid == 0) dbg_ns[0] = ptx::globaltimer_ns();
-    stage_frames_async(ch, 0);                          // in flight while the token side is prepared
-    // token side: thread (x, h) stages token x0+x for one contiguous share of the channels (coalesced
-    // over x) and sums its share of the row constants, channels ascending; the shares are then added
-    // in order.  nsh = how many threads serve a token (2 at 512 / 200).  The loop is kept SMALL: this
-    // is cold code that every warp runs once, and unrolled by 20 it was bound by instruction fetch
-    // (stall_no_inst, profiles/r1_ncu_logp.txt), not by the loads.
     const int nsh = max(1, min(4, nthr / tile_rows));
     const int dsh = ceil_div(D, nsh);
-    float *sPart = sL2 + F;                             // [nsh <= 4][2][tile_rows] partial row constants
     if (tid < nsh * tile_rows) {
         const int h = tid / tile_rows, x = tid - h * tile_rows, xg = x0 + x;
         const int d0 = h * dsh, d1 = min(D, d0 + dsh);
@@ -100,122 +80,157 @@ __device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, const T
                 const float m = __ldg(xm + (int64_t)d * T_x + xg);
                 const float ls = xl ? __ldg(xl + (int64_t)d * T_x + xg) : 0.f;
                 const float r = xl ? expf(-2.0f * ls) : 1.0f;         // models.py:363
-                sInv[d * tile_rows + x] = -0.5f * r;                    // models.py:368
-                sMiv[d * tile_rows + x] = m * r;                        // models.py:371
+                s.sInv[d * tile_rows + x] = -0.5f * r;                  // models.py:368
+                s.sMiv[d * tile_rows + x] = m * r;                      // models.py:371
                 l1 += kNegHalfLog2Pi - ls;                              // models.py:364-366
                 l4 = fmaf(-0.5f * (m * m), r, l4);                      // models.py:373-375
             }
         } else {
-            for (int d = d0; d < d1; ++d) sInv[d * tile_rows + x] = sMiv[d * tile_rows + x] = 0.f;
+            for (int d = d0; d < d1; ++d) s.sInv[d * tile_rows + x] = s.sMiv[d * tile_rows + x] = 0.f;
         }
-        sPart[(2 * h) * tile_rows + x] = l1;
-        sPart[(2 * h + 1) * tile_rows + x] = l4;
+        s.sPart[(2 * h) * tile_rows + x] = l1;
+        s.sPart[(2 * h + 1) * tile_rows + x] = l4;
     }
     __syncthreads();
     if (tid < tile_rows) {
-        float l1 = sPart[tid], l4 = sPart[tile_rows + tid];
+        float l1 = s.sPart[tid], l4 = s.sPart[tile_rows + tid];
         for (int h = 1; h < nsh; ++h) {
-            l1 += sPart[(2 * h) * tile_rows + tid];
-            l4 += sPart[(2 * h + 1) * tile_rows + tid];
+            l1 += s.sPart[(2 * h) * tile_rows + tid];
+            l4 += s.sPart[(2 * h + 1) * tile_rows + tid];
         }
-        sL1[tid] = l1;
-        sL4[tid] = l4;
+        s.sL1[tid] = l1;
+        s.sL4[tid] = l4;
     }
     __syncthreads();
-    if (dbg_ns && tid == 0) dbg_ns[8] = ptx::globaltimer_ns();
+}
+
+// mean_only: inv_var == 1, the inv_var term does not depend on the token (models.py:367-369 with
+// x_logs == 0): one sum per frame, channels ascending.  Ends with a CTA barrier.
+__device__ __forceinline__ void frame_sums_mean_only(const CtaSmem &s, int D, int F, int buf) {
+    if ((int)threadIdx.x < F) {
+        const float *zc = s.sZ + buf * D * F + threadIdx.x;
+        float l2 = 0.f;
+        for (int d = 0; d < D; ++d) {
+            const float zv = zc[d * F];
+            l2 = fmaf(-0.5f * zv, zv, l2);
+        }
+        s.sL2[threadIdx.x] = l2;
+    }
+    __syncthreads();
+}
+
+// Where a chunk's scores go: row x of the tile's utterance starts at out + x * row_stride; frame
+// y0 + j of the chunk lands in column col0 + j.  `keep_frames`: frames >= T_y of the last chunk are
+// skipped (the materialised matrix has no such columns) or stored (a ring row has room for the
+// whole chunk, and the sweep's boxes read it: they must be finite).
+struct ChunkOut {
+    float *out;
+    int64_t row_stride;
+    int col0;
+    bool all_frames;
+};
+
+// Contract chunk `ch` (already staged in buffer `buf`) of tile x0 and store the scores.
+// mode 2: contract, 1: store zeros (cells the sweep covers but never uses), 0: nothing -- per THREAD
+// (its four tokens x the chunk), decided by the caller's band test.
+__device__ __forceinline__ void contract_chunk(const LogpParams &p, const CtaSmem &s, const TileShape &t, int x0, int ch, int buf,
+                                               int mode, const ChunkOut &o) {
+    const int D = p.D, T_x = p.T_x, T_y = p.T_y, tile_rows = t.tile_rows, F = t.F, CG = t.CG;
+    const bool mean_only = p.x_logs == nullptr;
+    const int tid = threadIdx.x;
+    const int rg = tid / CG, cg = tid - rg * CG;        // 4 tokens x {4+4} frames per thread
+    if (rg >= t.RG || mode == 0) return;
     GemmAcc acc;
-    // One CTA barrier per chunk: it makes chunk k's frames visible, says that every warp is done with
-    // chunk k-1 (its frame buffer may be refilled, its scores are stored), and orders those stores
-    // before thread 0's release of chunk k-1's flag.
-    int ch_prev = ch;
+    if (mode == 1) {
+#pragma unroll
+        for (int i = 0; i < kGemmTM; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc.v[i][j] = 0ull;
+    } else if (mean_only) {
+        gemm_tile<true, true>(s.sInv, s.sMiv, s.sZ + buf * D * F, D, tile_rows, F, rg, cg, acc);
+    } else {
+        gemm_tile<true, false>(s.sInv, s.sMiv, s.sZ + buf * D * F, D, tile_rows, F, rg, cg, acc);
+    }
+    const int y0 = ch * F;
+#pragma unroll
+    for (int i = 0; i < kGemmTM; ++i) {
+        const int xr = rg * kGemmTM + i, x = x0 + xr;
+        if (x >= T_x) break;
+        const float l1 = s.sL1[xr], l4 = s.sL4[xr];
+        float *row = o.out + (int64_t)x * o.row_stride + o.col0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int yl = (F >> 1) * h + 4 * cg;
+            if (o.all_frames || y0 + yl < T_y) {            // T_y % 4 == 0: whole float4 or nothing
+                float c[4];
+                acc.quad(i, h, c);
+                float4 r;
+                if (mode == 1) {
+                    r = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else if (mean_only) {
+                    const float4 l2 = *reinterpret_cast<const float4 *>(s.sL2 + yl);
+                    r.x = logp_cell_finish_mean_only(l1, l2.x, c[0], l4);
+                    r.y = logp_cell_finish_mean_only(l1, l2.y, c[1], l4);
+                    r.z = logp_cell_finish_mean_only(l1, l2.z, c[2], l4);
+                    r.w = logp_cell_finish_mean_only(l1, l2.w, c[3], l4);
+                } else {
+                    r.x = logp_cell_finish(l1, c[0], l4);
+                    r.y = logp_cell_finish(l1, c[1], l4);
+                    r.z = logp_cell_finish(l1, c[2], l4);
+                    r.w = logp_cell_finish(l1, c[3], l4);
+                }
+                *reinterpret_cast<float4 *>(row + yl) = r;
+            }
+        }
+    }
+}
+
+// Single launch: only the sweep reads the scores, and only inside the reference's band
+// (core.pyx:18: max(0, t_x + y - t_y) <= x < min(t_x, y + 1)).  A thread whose four tokens are
+// outside the band for every frame of the chunk skips the contraction and stores zeros (the
+// sweep's boxes still cover those cells: they must be finite, their value is irrelevant); tokens
+// beyond t_x are not touched at all.  With full lengths (200 x 1000) that is 15 % of the cells,
+// with ragged batches whatever the padding is.
+__device__ __forceinline__ int band_mode(const TileShape &t, int x0, int ch, int band_tx, int band_ty) {
+    const int rg = threadIdx.x / t.CG;
+    const int y0 = ch * t.F, t0 = x0 + rg * kGemmTM;
+    const int lo = max(0, band_tx + y0 - band_ty), hi = min(band_tx, min(y0 + t.F, band_ty));
+    return (t0 >= band_tx) ? 0 : (t0 + kGemmTM > lo && t0 < hi) ? 2 : 1;
+}
+
+// chunks chunk_first, chunk_first + chunk_stride, ... (chunk_count of them) of token tile x0 of
+// utterance b; indices from skip_from up are shifted by skip_by (the chunks the spare CTAs take).
+// The materialising kernel's program: scores go to p.logp [B][T_x][T_y].
+__device__ __forceinline__ void logp_cta(const LogpParams &p, float *sm, const TileShape &t, int b, int x0, int chunk_first,
+                                         int chunk_stride, int chunk_count, int skip_from, int skip_by) {
+    if (chunk_count <= 0) return;
+    const int D = p.D, F = t.F;
+    const CtaSmem s = carve_smem(sm, D, t);
+    const bool mean_only = p.x_logs == nullptr;         // config.py:52, the reference default
+    ChunkOut o{p.logp + (int64_t)b * p.T_x * p.T_y, p.T_y, 0, false};
+
+    // the sequence is kept in un-shifted numbering; `ch` is the real chunk
+    int seq = chunk_first;
+    auto next_chunk = [&]() {
+        seq += chunk_stride;
+        return seq >= skip_from ? seq + skip_by : seq;
+    };
+    __syncthreads();                                    // a previous tile of this CTA is done with the shared memory
+    int ch = seq >= skip_from ? seq + skip_by : seq;
+    stage_frames_async(p, s, t, b, ch, 0);              // in flight while the token side is prepared
+    stage_tokens(p, s, t, b, x0);
+    // One CTA barrier per chunk: it makes chunk k's frames visible and says that every warp is done
+    // with chunk k-1 (its frame buffer may be refilled).
     for (int k = 0; k < chunk_count; ++k) {
         const int buf = k & 1;
-        const int ch_next = next_chunk(ch);
-        const bool more = k + 1 < chunk_count;
+        const int ch_next = next_chunk();
         ptx::cp_async_wait<0>();
         __syncthreads();
-        if (kSignal && k > 0 && tid == 0) {
-            __threadfence();                            // the CTA's scores (ordered by the barrier) before the flag
-            ptx::red_release_gpu_add(ready + ch_prev, 1);
-            if (dbg_ns) dbg_ns[k < 8 ? k : 7] = ptx::globaltimer_ns();
-        }
-        if (dbg_ns && tid == 0 && k < 3) dbg_ns[12 + k] = ptx::globaltimer_ns();
-        if (dbg_ns && tid == 0 && k == 0) dbg_ns[5] = clock64();
-        if (more) stage_frames_async(ch_next, buf ^ 1); // lands while this chunk is contracted
-        if (mean_only) {
-            // inv_var == 1: the inv_var term does not depend on the token (models.py:367-369 with
-            // x_logs == 0): one sum per frame, channels ascending
-            if (tid < F) {
-                const float *zc = sZ + buf * D * F + tid;
-                float l2 = 0.f;
-                for (int d = 0; d < D; ++d) {
-                    const float zv = zc[d * F];
-                    l2 = fmaf(-0.5f * zv, zv, l2);
-                }
-                sL2[tid] = l2;
-            }
-            __syncthreads();
-        }
-        int mode = 2;                                   // 2: contract, 1: store zeros, 0: nothing
-        if (banded) {
-            const int y0 = ch * F, t0 = x0 + rg * kGemmTM;
-            const int lo = max(0, band_tx + y0 - band_ty), hi = min(band_tx, min(y0 + F, band_ty));
-            mode = (y0 >= band_ty + 32 || t0 >= band_tx) ? 0 : (t0 + kGemmTM > lo && t0 < hi) ? 2 : 1;
-        }
-        if (worker && mode != 0) {
-            if (mode == 1) {
-#pragma unroll
-                for (int i = 0; i < kGemmTM; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc.v[i][j] = 0ull;
-            } else if (mean_only) {
-                gemm_tile<true, true>(sInv, sMiv, sZ + buf * D * F, D, tile_rows, F, rg, cg, acc);
-            } else {
-                gemm_tile<true, false>(sInv, sMiv, sZ + buf * D * F, D, tile_rows, F, rg, cg, acc);
-            }
-            if (dbg_ns && tid == 0 && k < 3) dbg_ns[9 + k] = ptx::globaltimer_ns();
-            if (dbg_ns && tid == 0 && k == 0) dbg_ns[6] = clock64();
-            const int y0 = ch * F;
-#pragma unroll
-            for (int i = 0; i < kGemmTM; ++i) {
-                const int xr = rg * kGemmTM + i, x = x0 + xr;
-                if (x >= T_x) break;
-                const float l1 = sL1[xr], l4 = sL4[xr];
-                float *row = out + (int64_t)x * T_y;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int yl = (F >> 1) * h + 4 * cg, y = y0 + yl;
-                    if (y < T_y) {                      // T_y % 4 == 0: whole float4 or nothing
-                        float c[4];
-                        acc.quad(i, h, c);
-                        float4 r;
-                        if (mode == 1) {
-                            r = make_float4(0.f, 0.f, 0.f, 0.f);
-                        } else if (mean_only) {
-                            const float4 l2 = *reinterpret_cast<const float4 *>(sL2 + yl);
-                            r.x = logp_cell_finish_mean_only(l1, l2.x, c[0], l4);
-                            r.y = logp_cell_finish_mean_only(l1, l2.y, c[1], l4);
-                            r.z = logp_cell_finish_mean_only(l1, l2.z, c[2], l4);
-                            r.w = logp_cell_finish_mean_only(l1, l2.w, c[3], l4);
-                        } else {
-                            r.x = logp_cell_finish(l1, c[0], l4);
-                            r.y = logp_cell_finish(l1, c[1], l4);
-                            r.z = logp_cell_finish(l1, c[2], l4);
-                            r.w = logp_cell_finish(l1, c[3], l4);
-                        }
-                        *reinterpret_cast<float4 *>(row + y) = r;
-                    }
-                }
-            }
-        }
-        ch_prev = ch;
+        if (k + 1 < chunk_count) stage_frames_async(p, s, t, b, ch_next, buf ^ 1);   // lands while this chunk is contracted
+        if (mean_only) frame_sums_mean_only(s, D, F, buf);
+        o.col0 = ch * F;
+        contract_chunk(p, s, t, x0, ch, buf, 2, o);
         ch = ch_next;
-    }
-    __syncthreads();                                    // everyone has stored the last chunk
-    if (kSignal && tid == 0) {
-        __threadfence();
-        ptx::red_release_gpu_add(ready + ch_prev, 1);
-        if (dbg_ns) dbg_ns[chunk_count < 8 ? chunk_count : 7] = ptx::globaltimer_ns();
     }
 }
 
@@ -310,17 +325,13 @@ __host__ __device__ inline bool deal_piece(const Deal &q, int pidx, int it, Deal
     return true;
 }
 
-// Runs CTA `pidx`'s share.  ready: [B][t.nchunks] counters (kSignal only).  The deal covers chunks
-// chunk_base .. t.nchunks - 1 of every row (q.nchunks == t.nchunks - chunk_base).  One call site of
-// logp_cta per kind of CTA: the program is a few thousand instructions and instruction fetch is not free.
-template <bool kSignal>
-__device__ __forceinline__ void run_deal(const LogpParams &p, float *sm, const TileShape &t, const Deal &q, int pidx, int *ready,
-                                         int chunk_base = 0, long long *dbg_ns = nullptr) {
+// Runs CTA `pidx`'s share (the materialising kernel).  One call site of logp_cta: the program is a
+// few thousand instructions and instruction fetch is not free.
+__device__ __forceinline__ void run_deal(const LogpParams &p, float *sm, const TileShape &t, const Deal &q, int pidx) {
     DealPiece o;
     for (int it = 0; deal_piece(q, pidx, it, o); ++it) {
         const int b = o.r / t.row_tiles, rt = o.r - b * t.row_tiles;
-        logp_cta<kSignal>(p, sm, t, b, rt * t.tile_rows, o.first, o.stride, o.count, o.skip_from, q.nchunks - q.cover, chunk_base,
-                          kSignal ? ready + (size_t)b * t.nchunks : nullptr, dbg_ns);
+        logp_cta(p, sm, t, b, rt * t.tile_rows, o.first, o.stride, o.count, o.skip_from, q.nchunks - q.cover);
     }
 }
 

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p, Plan plan) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int K = kCluster ? plan.K : 1;
-    dp_cta<R, kDbg, kCluster, false>(tmap, p, plan, smem, blockIdx.x / K, blockIdx.x, nullptr, 0);
+    dp_cta<R, kDbg, kCluster>(tmap, p, plan, smem, blockIdx.x / K, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -75,6 +75,11 @@ int mas_b200_debug_tile_shape(int T_x, int T_y, int32_t *out6);
  *     MAS_ERR_UNSUPPORTED_SHAPE when the TMA path cannot take the shape. */
 int mas_b200_debug_path_plan(int B, int T_x, int T_y, int max_smem, int num_sms, int32_t *out8);
 int mas_b200_debug_deal(int P, int BT, int nchunks, int32_t *owner, int32_t *order);
+/*   debug_fused_geom: kernel (2)'s geometry on such a device: out12 = {CTAs per utterance (cluster size),
+ *     tokens per sweep lane, tokens per CTA (bound), FFMA teams, warps per team, column groups, frames per
+ *     chunk, score-ring depth in 32-frame boxes, direction bits in shared memory?, shared memory bytes,
+ *     FFMA warps, rows per ring box}; MAS_ERR_UNSUPPORTED_SHAPE when the single launch cannot take the shape. */
+int mas_b200_debug_fused_geom(int B, int D, int T_x, int T_y, int max_smem, int num_sms, int32_t *out12);
 /* MAS_OK iff the current CUDA device can run the kernels (compute capability 10.x). */
 int mas_b200_device_ok(void);
 
