@@ -12,7 +12,7 @@ namespace mas {
 thread_local int g_last_cuda_error = 0;
 std::atomic<long long *> g_dbg_cycles{nullptr};
 }
-static std::atomic<int> g_force_unfused{0};   // testing hook: run the two kernels back to back
+static std::atomic<int> g_force_unfused{0};   // testing hook: 0 = by estimate, 1 = the two kernels, 2 = the single launch
 
 using namespace mas;
 
@@ -82,7 +82,7 @@ void mas_b200_debug_set_cycle_buffer(void *device_buffer) { g_dbg_cycles.store(s
 
 void mas_b200_debug_force_cluster(int ctas_per_utterance) { path_systolic_force_cluster(ctas_per_utterance); }
 
-void mas_b200_debug_force_unfused(int on) { g_force_unfused.store(on); }
+void mas_b200_debug_force_unfused(int mode) { g_force_unfused.store(mode); }
 
 int mas_b200_device_ok(void) {
     int dev = 0, major = 0;
@@ -178,11 +178,13 @@ int mas_b200_fused_maximum_path_f32(const float *x_m, const float *x_logs, const
         return MAS_ERR_INVALID_ARGUMENT;
     FusedWorkspace w = fused_ws(B, T_x, T_y);
     if (workspace == nullptr || workspace_bytes < mas_b200_fused_workspace_bytes(B, D, T_x, T_y)) return MAS_ERR_WORKSPACE_TOO_SMALL;
-    // One launch: producer CTAs (FFMA contraction) and sweep CTAs run concurrently (mas_fused.cu).
-    if (!g_force_unfused.load()) {
+    // One launch, a cluster of CTAs per utterance, scores produced and consumed in shared memory
+    // (mas_fused.cu) -- when its cost estimate for the shape beats the two kernels'.
+    const int mode = g_force_unfused.load();
+    if (mode != 1) {
         LogpParams lp{x_m, x_logs, z, nullptr, B, D, T_x, T_y};
         const int rc1 = launch_fused(lp, x_len, y_len, path, durations, frame_token, workspace, workspace_bytes, max_neg_val,
-                                     static_cast<cudaStream_t>(stream));
+                                     mode == 2, static_cast<cudaStream_t>(stream));
         if (rc1 != MAS_ERR_UNSUPPORTED_SHAPE) return rc1;
     }
     // Shapes the single launch does not take (frame count not a multiple of 4, > 80 channels, > 1024

@@ -112,9 +112,13 @@ __device__ __forceinline__ void cell_fast(float &stay, float adv, float l, uint3
 }
 
 // Four frames (one 16-byte group) of R tokens per lane.
-template <int R, bool kCluster>
+// kOut: where lane `publisher` hands its last token's four scores: 0 = this CTA's shared memory,
+// 1 = a shared::cluster address (plain remote store; the caller publishes progress with a release),
+// 2 = a shared::cluster address by st.async, completing 16 bytes on the remote mbarrier `bar_out`
+// (the consumer waits on that barrier: no fence on either side).
+template <int R, int kOut>
 __device__ __forceinline__ void sweep_group(const float4 (&L)[R], const float4 &b, float (&v)[R], uint32_t (&acc)[R],
-                                            float &carry, uint32_t bnd_out, bool publisher, int g) {
+                                            float &carry, uint32_t bnd_out, bool publisher, int g, uint32_t bar_out) {
     // scores of the previous warp's last token after frames col0+4g-1 .. col0+4g+2
     const float up4[4] = {carry, b.x, b.y, b.z};
     carry = b.w;
@@ -132,7 +136,9 @@ __device__ __forceinline__ void sweep_group(const float4 (&L)[R], const float4 &
     }
     // lane 31 hands its last token's four scores to the next warp (possibly in the next CTA: the
     // address is a shared::cluster one)
-    if (kCluster)
+    if (kOut == 2)
+        ptx::st_async_v4_if(publisher, bnd_out + g * 16, make_float4(out4[0], out4[1], out4[2], out4[3]), bar_out);
+    else if (kOut == 1)
         ptx::st_cluster_v4_if(publisher, bnd_out + g * 16, make_float4(out4[0], out4[1], out4[2], out4[3]));
     else
         ptx::st_shared_v4_if(publisher, bnd_out + g * 16, make_float4(out4[0], out4[1], out4[2], out4[3]));
@@ -170,9 +176,9 @@ __device__ __forceinline__ void zero_below_diagonal(float *tile, int lane, int r
 // The loop is software-pipelined by hand (group g+1 is fetched from shared memory while group g is
 // swept) and only unrolled twice: a DP warp runs alone on its scheduler, so nothing else hides a
 // shared-memory round trip or an instruction-cache miss.
-template <int R, bool kCluster>
+template <int R, int kOut>
 __device__ __forceinline__ void sweep_block(uint32_t tile, const uint32_t (&lane_c)[R], float (&v)[R], uint32_t (&acc)[R],
-                                            float &carry, uint32_t bin, uint32_t bnd_out, bool publisher) {
+                                            float &carry, uint32_t bin, uint32_t bnd_out, bool publisher, uint32_t bar_out = 0u) {
     // tile: shared address of the staged box; lane_c[i] = this lane's row i inside it with its
     // swizzle term folded in (rows are 128-byte aligned, so byte offset | swizzle): the 16-byte group g
     // of row i sits at q[i] ^ (g << 4) -- one LOP3 with an immediate per load (the generic-pointer form
@@ -190,13 +196,40 @@ __device__ __forceinline__ void sweep_block(uint32_t tile, const uint32_t (&lane
 #pragma unroll
         for (int i = 0; i < R; ++i) LB[i] = ptx::ld_shared_v4(q[i] ^ (uint32_t)((g + 1) << 4));
         bB = ptx::ld_shared_v4(bin + (g + 1) * 16);
-        sweep_group<R, kCluster>(LA, bA, v, acc, carry, bnd_out, publisher, g);
+        sweep_group<R, kOut>(LA, bA, v, acc, carry, bnd_out, publisher, g, bar_out);
         if (g + 2 < 8) {
 #pragma unroll
             for (int i = 0; i < R; ++i) LA[i] = ptx::ld_shared_v4(q[i] ^ (uint32_t)((g + 2) << 4));
             bA = ptx::ld_shared_v4(bin + (g + 2) * 16);
         }
-        sweep_group<R, kCluster>(LB, bB, v, acc, carry, bnd_out, publisher, g + 1);
+        sweep_group<R, kOut>(LB, bB, v, acc, carry, bnd_out, publisher, g + 1, bar_out);
+    }
+}
+
+// The same block with the shared-memory loads issued kAhead - 1 groups before their use: for a sweep
+// warp that shares its SM with warps saturating the shared-memory pipe (the fused launch), where a
+// load takes several times its idle latency.
+template <int R, int kOut, int kAhead>
+__device__ __forceinline__ void sweep_block_ahead(uint32_t tile, const uint32_t (&lane_c)[R], float (&v)[R], uint32_t (&acc)[R],
+                                                  float &carry, uint32_t bin, uint32_t bnd_out, bool publisher, uint32_t bar_out) {
+    uint32_t q[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) q[i] = tile + lane_c[i];
+    float4 L[kAhead][R], bq[kAhead];
+#pragma unroll
+    for (int a = 0; a < kAhead - 1; ++a) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) L[a][i] = ptx::ld_shared_v4(q[i] ^ (uint32_t)(a << 4));
+        bq[a] = ptx::ld_shared_v4(bin + a * 16);
+    }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        if (g + kAhead - 1 < 8) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) L[(g + kAhead - 1) % kAhead][i] = ptx::ld_shared_v4(q[i] ^ (uint32_t)((g + kAhead - 1) << 4));
+            bq[(g + kAhead - 1) % kAhead] = ptx::ld_shared_v4(bin + (g + kAhead - 1) * 16);
+        }
+        sweep_group<R, kOut>(L[g % kAhead], bq[g % kAhead], v, acc, carry, bnd_out, publisher, g, bar_out);
     }
 }
 
@@ -508,7 +541,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
                     __syncwarp();
                 }
                 const long long t4 = kDbg ? clock64() : 0;
-                sweep_block<R, kCluster>(tile_a, lane_c, v, acc, carry, bnd_in_a + ring_slot, bnd_out_base + ring_slot, publisher);
+                sweep_block<R, kCluster ? 1 : 0>(tile_a, lane_c, v, acc, carry, bnd_in_a + ring_slot, bnd_out_base + ring_slot, publisher);
                 if (kDbg) t_core += clock64() - t4;
 #pragma unroll
                 for (int i = 0; i < R; ++i) acc[i] = __brev(acc[i]);   // first frame came in first: bit 31 -> bit 0

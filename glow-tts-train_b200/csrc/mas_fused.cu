@@ -11,15 +11,19 @@
 //     128-byte-swizzled layout kernel (1) stages with TMA.  The warps work in independent TEAMS with a
 //     named barrier each (chunk j belongs to team j mod nteams), so that finished scores appear every
 //     F frames instead of every nteams x F.  The token-side operands (-0.5 exp(-2 logs), m exp(-2 logs))
-//     stay in shared memory for the whole utterance; z arrives in panels of 16 channels by cp.async,
-//     double-buffered per team.  Arithmetic, operand order and the row constants' summation order are
-//     those of the materialising kernel (mas_logp_cta.cuh): bit-identical scores.
+//     stay in shared memory for the whole utterance; z arrives in panels of 16 channels by TMA
+//     (one elected thread per team issues [16 channels x F frames] boxes into a 3-stage ring with
+//     full/empty mbarriers: no thread spends an instruction on staging, no barrier per panel).
+//     Arithmetic, operand order and the row constants' summation order are those of the
+//     materialising kernel (mas_logp_cta.cuh): bit-identical scores.
 //   * ONE sweep warp (warp 0) runs kernel (1)'s recurrence (mas_dp_cta.cuh: sweep_block) over the
 //     ring, 32 frames per step: waits for the teams' chunk counters (shared memory, acquire), takes the
 //     score of the slice's predecessor token from the previous CTA's sweep through distributed shared
-//     memory and hands its own last token's to the next CTA, packs the direction bits, frees the box
-//     (`consumed`, the producers' back-pressure), and drips bulk copies of a zero page into the dense
-//     output on the way.
+//     memory and hands its own last token's to the next CTA (st.async into the neighbour's 16-block
+//     boundary ring, completing bytes on the neighbour's mbarrier: data and signal in one message, no
+//     fence in the loop; credits come back as a plain remote store), packs the direction bits, frees
+//     the box (`consumed`, the producers' back-pressure), and drips bulk copies of a zero page into
+//     the dense output on the way.
 //   * backtrack by tokens, CTA K-1 -> 0 over DSMEM; ones, durations, frame -> token by all threads.
 // Only the cells the reference's band touches are ever contracted (core.pyx:18): a slice starts at
 // the 32-frame block of its first token and ends where its last token leaves the band.
@@ -31,7 +35,9 @@
 // Shapes the launch does not take (frame count not a multiple of 4, more than 80 channels, slices
 // that do not fit an SM) run as the two kernels back to back over groups of utterances (mas_api.cu).
 #include <cuda.h>
+#include <cudaTypedefs.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -48,14 +54,18 @@ using systolic::kSpinLimit;
 
 constexpr int kThreads = 512;
 constexpr int kChan = 16;              // channels per staged panel of z
+constexpr int kStages = 3;             // z panels in flight per team
 constexpr int kZeroPage = 8192;        // bytes of zeros the dense output is filled from
 constexpr int kMaxTeams = 8;
 constexpr int kBarFfma = 15;           // named barrier of all FFMA threads; teams use 1 .. nteams
+constexpr int kBarSums = 14;           // ... of the warps that sum the row constants
 constexpr int kMaxClusters = 192;      // workspace bound (no device query in the size function)
 
 // control words in shared memory (ints)
-enum Ctl { kTeamDone = 0, kConsumed = 8, kDonePrev = 9, kDoneSelf = 10, kDoneNext = 11, kBtFlag = 12, kBtToken = 13,
-           kBtFrame = 14, kRedo = 15, kCtlInts = 16 };
+// kTeamDone[t]: warps of team t x chunks they have stored; kConsumed: boxes swept; kCredit: blocks of
+// this CTA's boundary scores the next CTA has consumed (written remotely)
+// kBtToken / kBtFrame: the backtrack's hand-over from the CTA above (one 8-byte st.async)
+enum Ctl { kTeamDone = 0, kConsumed = 8, kCredit = 11, kBtToken = 12, kBtFrame = 13, kRedo = 15, kCtlInts = 16 };
 
 struct Geom {
     int K, NC;                         // CTAs per cluster, clusters in the grid
@@ -65,9 +75,13 @@ struct Geom {
     int CG_cap, F_cap;                 // column groups / frames per chunk (bound)
     int NB;                            // score ring depth in 32-frame boxes
     int nblk, bits_in_smem;
+    int ops_tmp3;                      // the ring has room for stage_ops' third scratch array (exp(-2 logs))
+    int passes;                        // contraction passes of a full-length utterance (host estimate)
     int nsh, dsh;                      // channel shares of the row constants, as the materialising kernel sums them
-    int off_zero, off_bnd, off_run, off_ctl, off_big, off_ops, off_l14, off_part, off_z, off_l2, off_ring, off_bits, total;
+    int off_zero, off_bnd, off_run, off_xend, off_ctl, off_bar, off_big, off_ops, off_l14, off_part, off_z, off_l2, off_ring, off_bits,
+        off_maps, total;
     uint32_t *ws_bits;                 // [NC][K][nblk][ring_rows] when the bits do not fit shared memory
+    unsigned char *ws_maps;            // ... and the backtrack's block maps [NC][K][nblk][ring_rows] bytes with them
     float *redo_scratch;               // [NC][T_x][t_ref.F]
     uint32_t *redo_bits;               // [NC][nblk][T_x + 64]
     TileShape t_ref;                   // the materialising kernel's tile (row-constant shares, redo)
@@ -81,6 +95,7 @@ struct Utt {
     int x0, n_real;                    // first token / real tokens of this CTA's slice
     int TR, RG, CG, F;                 // contraction tile: TR = 4 RG rows, chunks of F = 8 CG frames
     int cb0, cbend;                    // 32-frame blocks the slice is in the band for (cbend < cb0: none)
+    int f_lo, f_hi;                    // frames [f_lo, f_hi) are contracted: the band of the slice, to multiples of 8
     int nch;                           // chunks to contract
 };
 
@@ -92,48 +107,83 @@ __device__ __forceinline__ void st_release_shared(int *p, int v) { ptx::st_relea
 // FFMA side
 // ---------------------------------------------------------------------------------------------
 
-// Token-side operands of the slice, by all FFMA threads (fidx of nffma).  The element-wise part is
-// spread over every thread; the row constants are summed the way mas_logp_cta.cuh::stage_tokens does
-// (nsh shares of dsh channels, ascending inside a share, shares added in order) from the same
-// expressions, so that they are bit-identical (the second pass re-reads its operands from L1).
-__device__ __forceinline__ void stage_ops(const Geom &g, const Utt &u, const LogpParams &p, unsigned char *smem, int fidx, int nffma) {
+// Token-side operands of the slice, by all FFMA threads (fidx of nffma).  This is the cold start of
+// the utterance and nothing else hides the first touch of x_m / x_logs, so the raw values come in
+// with ONE round of 4-byte cp.async (a slice starts at any token: no 16-byte alignment) into the
+// still empty score ring, and everything else reads shared memory: the element-wise operands by
+// all threads, the row constants summed the way mas_logp_cta.cuh::stage_tokens does (nsh shares of
+// dsh channels, ascending inside a share, shares added in order) from the same expressions, so
+// that they are bit-identical.
+__device__ __forceinline__ void stage_ops(const Geom &g, const Utt &u, const LogpParams &p, unsigned char *smem, int fidx, int nffma,
+                                          long long *dbg) {
     const int D = p.D, T_x = p.T_x, TR = u.TR;
     float *sInv = reinterpret_cast<float *>(smem + g.off_ops), *sMiv = sInv + D * TR;
     float *sL1 = reinterpret_cast<float *>(smem + g.off_l14), *sL4 = sL1 + g.tr_max;
     float *sPart = reinterpret_cast<float *>(smem + g.off_part);
+    // raw m (then -0.5 m^2), logs, exp(-2 logs): [D][TR] each
+    float *tM = reinterpret_cast<float *>(smem + g.off_ring), *tL = tM + D * TR, *tR = tL + D * TR;
     const float *xm = p.x_m + (int64_t)u.b * D * T_x + u.x0;
     const float *xl = p.x_logs ? p.x_logs + (int64_t)u.b * D * T_x + u.x0 : nullptr;
-    for (int e = fidx; e < D * TR; e += nffma) {
-        const int d = e / TR, x = e - d * TR;
-        float inv = 0.f, miv = 0.f;
-        if (x < u.n_real) {
-            const float m = __ldg(xm + (int64_t)d * T_x + x);
-            const float ls = xl ? __ldg(xl + (int64_t)d * T_x + x) : 0.f;
-            const float r = xl ? expf(-2.0f * ls) : 1.0f;         // models.py:363
-            inv = -0.5f * r;                                        // models.py:368
-            miv = m * r;                                            // models.py:371
+    const int total = D * TR;
+    // element e = fidx + k nffma is (channel d, token x): stepped without a division per element
+    const int d_first = fidx / TR, x_first = fidx - d_first * TR, d_step = nffma / TR, x_step = nffma - d_step * TR;
+    {
+        int d = d_first, x = x_first;
+        for (int e = fidx; e < total; e += nffma) {
+            if (x < u.n_real) {
+                ptx::cp_async_4(tM + e, xm + (int64_t)d * T_x + x);
+                if (xl) ptx::cp_async_4(tL + e, xl + (int64_t)d * T_x + x);
+            }
+            d += d_step, x += x_step;
+            if (x >= TR) x -= TR, ++d;
         }
-        sInv[e] = inv;
-        sMiv[e] = miv;
     }
+    ptx::cp_async_commit();
+    ptx::cp_async_wait<0>();
+    named_sync(kBarFfma, nffma);
+    if (dbg && fidx == 0) dbg[26] = ptx::globaltimer_ns();
+    {
+        int x = x_first;
+        for (int e = fidx; e < total; e += nffma) {
+            float inv = 0.f, miv = 0.f;
+            if (x < u.n_real) {
+                const float m = tM[e];
+                const float r = xl ? expf(-2.0f * tL[e]) : 1.0f;      // models.py:363
+                inv = -0.5f * r;                                      // models.py:368
+                miv = m * r;                                          // models.py:371
+                tM[e] = -0.5f * (m * m);
+                if (g.ops_tmp3) tR[e] = r;
+            }
+            sInv[e] = inv;
+            sMiv[e] = miv;
+            x += x_step;
+            if (x >= TR) x -= TR;
+        }
+    }
+    named_sync(kBarFfma, nffma);
+    if (dbg && fidx == 0) dbg[27] = ptx::globaltimer_ns();
+    // The row constants are not needed before the first chunk is finished (a whole contraction pass
+    // away): only the warps that sum them stay; the others start contracting.  (team_contract meets
+    // them at the FFMA barrier before its first store.)
+    const int sum_threads = ((g.nsh * TR + 31) & ~31) < nffma ? ((g.nsh * TR + 31) & ~31) : nffma;
+    if (fidx >= sum_threads) return;
     if (fidx < g.nsh * TR) {
         const int h = fidx / TR, x = fidx - h * TR;
         const int d0 = h * g.dsh, d1 = min(D, d0 + g.dsh);
         float l1 = 0.f, l4 = 0.f;
         if (x < u.n_real) {
-#pragma unroll 4
+#pragma unroll 8
             for (int d = d0; d < d1; ++d) {
-                const float m = __ldg(xm + (int64_t)d * T_x + x);
-                const float ls = xl ? __ldg(xl + (int64_t)d * T_x + x) : 0.f;
-                const float r = xl ? expf(-2.0f * ls) : 1.0f;
+                const float ls = xl ? tL[d * TR + x] : 0.f;
                 l1 += kNegHalfLog2Pi - ls;                          // models.py:364-366
-                l4 = fmaf(-0.5f * (m * m), r, l4);                  // models.py:373-375
+                const float r = !xl ? 1.0f : g.ops_tmp3 ? tR[d * TR + x] : expf(-2.0f * ls);   // (no room: the same expression again)
+                l4 = fmaf(tM[d * TR + x], r, l4);                   // models.py:373-375: -0.5 m^2 exp(-2 logs)
             }
         }
         sPart[(2 * h) * TR + x] = l1;
         sPart[(2 * h + 1) * TR + x] = l4;
     }
-    named_sync(kBarFfma, nffma);
+    named_sync(kBarSums, sum_threads);
     if (fidx < TR) {
         float l1 = sPart[fidx], l4 = sPart[TR + fidx];
         for (int h = 1; h < g.nsh; ++h) {
@@ -143,42 +193,68 @@ __device__ __forceinline__ void stage_ops(const Geom &g, const Utt &u, const Log
         sL1[fidx] = l1;
         sL4[fidx] = l4;
     }
-    named_sync(kBarFfma, nffma);
 }
 
+// The z panels of one team: a kStages-deep ring of [kChan channels][F frames] boxes, loaded by TMA.
+// Panel n of the team's sequence (its chunks in order, npan panels each) lives in stage n % kStages.
+struct ZPipe {
+    uint32_t full_a, empty_a;          // shared addresses of full[kStages], empty[kStages]
+    float *buf;                        // [kStages][kChan][F]
+    int stage_floats;
+    uint32_t box_bytes;
+};
+
 // One team's share of the slice's chunks: chunk j = team, team + nteams, ...  ttid of tn threads.
+// `seq0`: panels this team has already consumed in this launch (the mbarrier phases run on across
+// utterances).  Returns the new count.
 template <bool kMeanOnly>
-__device__ __forceinline__ void team_contract(const Geom &g, const Utt &u, const LogpParams &p, unsigned char *smem, int *ctl,
-                                              int team, int ttid, int tn) {
-    if (team >= u.nch) return;
-    const int D = p.D, T_y = p.T_y, F = u.F, CG = u.CG, TR = u.TR, NB = g.NB;
+__device__ __forceinline__ int team_contract(const CUtensorMap &tmap_z, const Geom &g, const Utt &u, const LogpParams &p,
+                                             unsigned char *smem, int *ctl, int team, int ttid, int tn, int seq0, bool prologue) {
+    if (team >= u.nch) {                                    // more teams than chunks
+        if (!prologue) named_sync(kBarFfma, g.nteams * tn);   // (the barrier the others pass before their first store)
+        return seq0;
+    }
+    const int D = p.D, F = u.F, CG = u.CG, TR = u.TR, NB = g.NB;
     const float *sInv = reinterpret_cast<const float *>(smem + g.off_ops), *sMiv = sInv + D * TR;
     const float *sL1 = reinterpret_cast<const float *>(smem + g.off_l14), *sL4 = sL1 + g.tr_max;
-    float *sZ = reinterpret_cast<float *>(smem + g.off_z) + (size_t)team * 2 * kChan * g.F_cap;   // [2][kChan][F]
     float *sL2 = reinterpret_cast<float *>(smem + g.off_l2) + team * g.F_cap;
     const uint32_t ring_a = ptx::smem_u32(smem + g.off_ring), box_bytes = (uint32_t)g.ring_rows * 128u;
+    ZPipe zp;
+    zp.stage_floats = kChan * g.F_cap;
+    zp.buf = reinterpret_cast<float *>(smem + g.off_z) + (size_t)team * kStages * zp.stage_floats;
+    zp.full_a = ptx::smem_u32(smem + g.off_bar) + (uint32_t)(team * 2 * kStages) * 8u;
+    zp.empty_a = zp.full_a + kStages * 8u;
+    zp.box_bytes = (uint32_t)zp.stage_floats * 4u;
     const int bar = 1 + team;
+    const int lane = ttid & 31;
     const int rg = ttid / CG, cg = ttid - rg * CG;
     const bool worker = rg < u.RG;
-    const float *zg = p.z + (int64_t)u.b * D * T_y;
-    const int f_begin = u.cb0 * kBlk;
-    const int total_rel = (u.cbend - u.cb0 + 1) * kBlk;     // frames the sweep reads, from f_begin
     const int npan = ceil_div(D, kChan);
-    const int f4 = F >> 2;
-    const int *consumed = ctl + kConsumed;
-    auto stage = [&](int j, int pd, int buf) {
-        const int y0 = f_begin + j * F, d0 = pd * kChan, cnt = min(kChan, D - d0);
-        float *dst = sZ + buf * kChan * g.F_cap;
-        for (int i = ttid; i < cnt * f4; i += tn) {
-            const int d = i / f4, k4 = (i - d * f4) << 2, y = y0 + k4;
-            ptx::cp_async_16(dst + d * F + k4, zg + (int64_t)(d0 + d) * T_y + (y < T_y ? y : 0), y < T_y);
-        }
-        ptx::cp_async_commit();
-    };
-    int buf = 0, count = 0;
-    bool announce = false;                                  // the previous chunk's stores are not yet published
+    const int my_chunks = (u.nch - team + g.nteams - 1) / g.nteams;
+    const int total_n = my_chunks * npan;
+    const volatile int *consumed = ctl + kConsumed;
     uint32_t spins = 0;
-    stage(team, 0, 0);
+    // panel k of this utterance (sequence number seq0 + k): wait until every warp of the team has
+    // handed the stage back, then arm `full` and issue the box
+    auto issue = [&](int k) {
+        if (k >= total_n) return;
+        const int n = seq0 + k, st = n % kStages;
+        if (n >= kStages) {
+            const uint32_t parity = (uint32_t)((n / kStages - 1) & 1);
+            while (!ptx::mbar_try_wait_a(zp.empty_a + st * 8u, parity))
+                if (++spins > kSpinLimit) systolic::spin_fail();
+        }
+        const int jj = team + (k / npan) * g.nteams, pd = k - (k / npan) * npan;
+        ptx::mbar_arrive_expect_tx_a(zp.full_a + st * 8u, zp.box_bytes);
+        ptx::tma_load_3d_a(ptx::smem_u32(zp.buf + st * zp.stage_floats), &tmap_z, zp.full_a + st * 8u, u.f_lo + jj * F, pd * kChan, u.b);
+    };
+    if (prologue) {
+        // the first panels, issued before the token side is staged (they land meanwhile)
+        if (ttid == 0)
+            for (int k = 0; k < kStages - 1; ++k) issue(k);
+        return seq0;
+    }
+    int k = 0, count = 0;
     for (int j = team; j < u.nch; j += g.nteams) {
         GemmAcc acc;
 #pragma unroll
@@ -186,24 +262,12 @@ __device__ __forceinline__ void team_contract(const Geom &g, const Utt &u, const
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc.v[i][q] = 0ull;
         float l2 = 0.f;
-        for (int pd = 0; pd < npan; ++pd) {
-            if (pd == npan - 1 && ttid == 0) {
-                // back-pressure: the boxes this chunk is stored into must have been swept
-                const int bx_last = (min(total_rel, j * F + F) - 1) >> 5;
-                while (ld_acquire_shared(consumed) + NB <= bx_last) {
-                    __nanosleep(64);
-                    if (++spins > kSpinLimit) systolic::spin_fail();
-                }
-            }
-            ptx::cp_async_wait<0>();
-            named_sync(bar, tn);                            // the panel has landed; everyone is done with the other buffer
-            if (announce && ttid == 0) st_release_shared(ctl + kTeamDone + team, count);   // (stores ordered by the barrier)
-            announce = false;
-            if (pd + 1 < npan)
-                stage(j, pd + 1, buf ^ 1);
-            else if (j + g.nteams < u.nch)
-                stage(j + g.nteams, 0, buf ^ 1);
-            const float *zb = sZ + buf * kChan * g.F_cap;
+        for (int pd = 0; pd < npan; ++pd, ++k) {
+            if (ttid == 0) issue(k + kStages - 1);          // (its stage was panel k-1's: this very warp handed it back last)
+            const int n = seq0 + k, st = n % kStages;
+            while (!ptx::mbar_try_wait_a(zp.full_a + st * 8u, (uint32_t)((n / kStages) & 1)))
+                if (++spins > kSpinLimit) systolic::spin_fail();
+            const float *zb = zp.buf + st * zp.stage_floats;
             const int d0 = pd * kChan, cnt = min(kChan, D - d0);
             if (worker) {
                 if (cnt == kChan)
@@ -217,14 +281,22 @@ __device__ __forceinline__ void team_contract(const Geom &g, const Utt &u, const
                     l2 = fmaf(-0.5f * zv, zv, l2);
                 }
             }
-            buf ^= 1;
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_a(zp.empty_a + st * 8u);
         }
-        if (kMeanOnly) {
-            if (ttid < F) sL2[ttid] = l2;
-            named_sync(bar, tn);
+        if (ttid == 0) {
+            // back-pressure: the boxes this chunk is stored into must have been swept
+            const int bx_last = ((min(u.f_hi, u.f_lo + j * F + F) - 1) >> 5) - u.cb0;
+            while (*consumed + NB <= bx_last) {
+                __nanosleep(64);
+                if (++spins > kSpinLimit) systolic::spin_fail();
+            }
         }
+        if (kMeanOnly && ttid < F) sL2[ttid] = l2;
+        if (count == 0) named_sync(kBarFfma, g.nteams * tn);   // the row constants are summed (stage_ops)
+        named_sync(bar, tn);                                // the ring has room (and the frame sums are there)
         if (worker) {
-            const int relb = j * F;
+            const int fb = u.f_lo + j * F;                  // the chunk's first frame
 #pragma unroll
             for (int i = 0; i < kGemmTM; ++i) {
                 const int xr = rg * kGemmTM + i;
@@ -232,8 +304,8 @@ __device__ __forceinline__ void team_contract(const Geom &g, const Utt &u, const
                 const uint32_t row_a = ring_a + (uint32_t)xr * 128u;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int yl = (F >> 1) * h + 4 * cg, relf = relb + yl;
-                    if (relf >= total_rel) continue;        // beyond the last box the sweep reads
+                    const int yl = (F >> 1) * h + 4 * cg, f = fb + yl;
+                    if (f >= u.f_hi) continue;              // beyond the band
                     float cq[4];
                     acc.quad(i, h, cq);
                     float4 r;
@@ -249,16 +321,17 @@ __device__ __forceinline__ void team_contract(const Geom &g, const Utt &u, const
                         r.z = logp_cell_finish(l1, cq[2], l4);
                         r.w = logp_cell_finish(l1, cq[3], l4);
                     }
-                    const int bx = relf >> 5, slot = bx % NB, gq = (relf & 31) >> 2;
+                    const int bx = (f >> 5) - u.cb0, slot = bx % NB, gq = (f & 31) >> 2;
                     ptx::st_shared_v4_if(true, row_a + (uint32_t)slot * box_bytes + (uint32_t)((gq ^ (xr & 7)) << 4), r);
                 }
             }
         }
         ++count;
-        announce = true;
+        // this warp's part of the chunk is stored: count it (release: the sweep reads the counter with acquire)
+        __syncwarp();
+        if (lane == 0) ptx::red_release_shared_add(ctl + kTeamDone + team, 1);
     }
-    named_sync(bar, tn);
-    if (ttid == 0) st_release_shared(ctl + kTeamDone + team, count);
+    return seq0 + total_n;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -305,28 +378,48 @@ struct ZeroFill {
 };
 
 // Returns non-zero when a real token of the slice ended with a non-finite score.
+//
+// Boundary protocol between the sweeps of neighbouring CTAs (token x0-1 of the previous CTA feeds
+// token x0 of this one): the previous CTA's publisher lane sends the four scores of every 16-byte
+// group with st.async into THIS CTA's boundary ring (kBndBlocks slots of 32 frames), each store
+// completing its bytes on the slot's mbarrier here; this warp arms a slot with arrive.expect_tx(128),
+// waits for its phase, sweeps, re-arms it and returns a credit (a plain remote store of the number
+// of consumed blocks -- it only guards the slot's reuse).  The previous CTA publishes blocks
+// [max(its first block, my first block - 1), its last block]; beyond its last block the boundary
+// token has left the band and whatever finite values the slot holds are never used.
 template <int R, bool kDbg>
 __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned char *smem, int *ctl, float neg, ZeroFill &zf,
                                            uint32_t *bits_g, long long *dbg) {
     const int lane = threadIdx.x & 31;
     const void *zero_page = smem + g.off_zero;
     int nonfinite = 0;
+    // the dense output's zeros: all bulk copies now, while the sweep has nothing to do yet (the first
+    // chunk of scores is a whole contraction pass away); they drain in the background
+    if (lane == 0) zf.drip(zero_page, 0x7fffffff);
+    long long t_chunks = 0, t_prev = 0, t_credit = 0, t_core = 0, t_bits = 0, t_done = 0, t_fill = 0, t_begin = 0;
+    if (kDbg) t_begin = clock64();
     if (u.cbend >= u.cb0) {
         float v[R];
         uint32_t acc[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) v[i] = neg;
         float carry = (u.x0 == 0) ? 0.f : neg;              // frame 0 of token 0 starts from 0 (core.pyx:24-25)
-        const bool has_next = u.x0 + u.n_c < u.tx;          // the next CTA has real tokens
-        const bool publisher = has_next && lane == u.n_c / R - 1;   // owns the slice's last token (n_c % R == 0)
         const uint32_t bnd_a = ptx::smem_u32(smem + g.off_bnd);
+        const uint32_t bnd_bar_a = ptx::smem_u32(smem + g.off_bar) + (uint32_t)(g.nteams * 2 * kStages) * 8u;   // [kBndBlocks]
+        // ---- as the producer of the next CTA's boundary ----
+        const bool has_next = u.x0 + u.n_c < u.tx;          // the next CTA has real tokens
+        const int pub_first = max(u.cb0, ((u.x0 + u.n_c) >> 5) - 1);
+        const bool pub_lane = lane == u.n_c / R - 1;        // owns the slice's last token (n_c % R == 0)
         const uint32_t bnd_out_base = has_next ? ptx::mapa(bnd_a, (uint32_t)(u.c + 1)) : 0u;
-        const uint32_t done_prev_a = ptx::smem_u32(ctl + kDonePrev), done_next_a = ptx::smem_u32(ctl + kDoneNext);
-        // my consumption -> the previous CTA's `done next`; my production -> the next CTA's `done prev`
-        const uint32_t mirror_prev = (u.c > 0) ? ptx::mapa(done_next_a, (uint32_t)(u.c - 1)) : 0u;
-        const uint32_t mirror_next = has_next ? ptx::mapa(done_prev_a, (uint32_t)(u.c + 1)) : 0u;
-        int seen_prev = (u.c > 0) ? -1 : kDoneAll;
-        int seen_next = has_next ? -1 : kDoneAll;
+        const uint32_t bar_out_base = has_next ? ptx::mapa(bnd_bar_a, (uint32_t)(u.c + 1)) : 0u;
+        const volatile int *credit = ctl + kCredit;         // blocks the next CTA has consumed (set to pub_first before the sweep)
+        int seen_credit = pub_first;
+        // ---- as the consumer of the previous CTA's ----
+        const int prev_x0 = u.x0 - u.n_c;
+        const int prev_first = (u.c > 0) ? max(prev_x0 >> 5, u.cb0 - 1) : 0x3fffffff;
+        const int prev_last = (u.c > 0) ? min(u.ty - 1, u.x0 - 1 + (u.ty - u.tx)) >> 5 : -1;
+        const uint32_t credit_out = (u.c > 0) ? ptx::mapa(ptx::smem_u32(ctl + kCredit), (uint32_t)(u.c - 1)) : 0u;
+        uint32_t phase_bits = 0u;                           // parity of every boundary slot's next phase
         const int row0 = u.x0 + lane * R;
         const int x_last = u.x0 + u.n_real - 1;
         uint32_t lane_c[R];
@@ -338,35 +431,63 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
         const uint32_t ring_a = ptx::smem_u32(smem + g.off_ring), box_bytes = (uint32_t)g.ring_rows * 128u;
         uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem + g.off_bits);
         uint32_t *bits_p = (g.bits_in_smem ? bits_s : bits_g) + (size_t)u.cb0 * g.ring_rows + lane * R;
-        const bool notifier = lane == u.n_c / R - 1;       // wrote the boundary scores, so it publishes the progress
+        int jn_team = 0, jn_need = g.team_warps, jn_end = u.f_lo + u.F;    // the chunk the sweep is waiting for
+        int ready_end = u.f_lo;                                              // frames below are known to be stored
         int slot = 0;
         uint32_t spins = 0;
+        // consume boundary block cb: wait for its bytes; afterwards (done) re-arm the slot and return the credit
+        auto bnd_wait = [&](int cb) {
+            const uint32_t s = (uint32_t)cb & (kBndBlocks - 1);
+            while (!ptx::mbar_try_wait_a(bnd_bar_a + s * 8u, (phase_bits >> s) & 1u))
+                if (++spins > kSpinLimit) systolic::spin_fail();
+            phase_bits ^= 1u << s;
+        };
+        auto bnd_done = [&](int cb) {
+            const uint32_t s = (uint32_t)cb & (kBndBlocks - 1);
+            if (lane == 0) {
+                ptx::mbar_arrive_expect_tx_a(bnd_bar_a + s * 8u, kBlk * 4);
+                ptx::st_cluster_u32(credit_out, (uint32_t)(cb + 1));
+            }
+        };
+        if (prev_first == u.cb0 - 1 && prev_first >= 0) {
+            // score of token x0-1 at the last frame before my first block (when the previous CTA swept that
+            // block; if its slice starts in my first block, that cell is below the diagonal: -1e9 already)
+            bnd_wait(prev_first);
+            carry = ptx::ld_shared_f32_a(bnd_a + (uint32_t)(((prev_first & (kBndBlocks - 1)) * kBlk + (kBlk - 1)) * 4));
+            __syncwarp();
+            bnd_done(prev_first);
+        }
         for (int cb = u.cb0; cb <= u.cbend; ++cb) {
-            while (seen_prev <= cb) {                       // the previous CTA's sweep has published block cb
-                seen_prev = ptx::ld_acquire_cluster_shared_a(done_prev_a);
-                if (seen_prev <= cb) __nanosleep(32);
-                if (++spins > kSpinLimit) systolic::spin_fail();
+            const long long t0 = kDbg ? clock64() : 0;
+            if (cb >= prev_first && cb <= prev_last) bnd_wait(cb);
+            const long long t1 = kDbg ? clock64() : 0;
+            const bool publishes = has_next && cb >= pub_first;
+            if (publishes) {
+                while (seen_credit + kBndBlocks <= cb) {    // the next CTA has consumed block cb - ring depth
+                    seen_credit = *credit;
+                    if (++spins > kSpinLimit) systolic::spin_fail();
+                }
             }
-            while (seen_next + kBndBlocks <= cb) {          // the next CTA's sweep has consumed block cb - ring depth
-                seen_next = ptx::ld_acquire_cluster_shared_a(done_next_a);
-                if (seen_next + kBndBlocks <= cb) __nanosleep(32);
-                if (++spins > kSpinLimit) systolic::spin_fail();
-            }
-            {   // this CTA's teams have stored the chunks the box spans
-                const int rel0 = (cb - u.cb0) * kBlk;
-                const int j0 = rel0 / u.F, j1 = min((rel0 + kBlk - 1) / u.F, u.nch - 1);
-                for (int j = j0; j <= j1; ++j) {
-                    const int team = j % g.nteams, need = j / g.nteams + 1;
-                    while (ld_acquire_shared(ctl + kTeamDone + team) < need) {
-                        __nanosleep(64);
+            const long long t2 = kDbg ? clock64() : 0;
+            const int last = min(cb * kBlk + kBlk, u.f_hi) - 1;
+            if (last >= ready_end) {
+                // this CTA's teams have stored the chunks up to the box's last frame (chunk jn ends at jn_end;
+                // chunk j is stored when every warp of team j % nteams has counted j / nteams + 1 chunks)
+                for (;;) {
+                    while (ld_acquire_shared(ctl + kTeamDone + jn_team) < jn_need) {
+                        __nanosleep(32);
                         if (++spins > kSpinLimit) systolic::spin_fail();
+                    }
+                    ready_end = jn_end;
+                    if (last < jn_end) break;
+                    jn_end += u.F;
+                    if (++jn_team == g.nteams) {
+                        jn_team = 0;
+                        jn_need += g.team_warps;
                     }
                 }
             }
-            // score of token x0-1 at the last frame before this block -- when the previous CTA swept that
-            // block; if its slice starts in this very block, that cell is below the diagonal: -1e9 already
-            if (cb == u.cb0 && u.cb0 > ((u.x0 - u.n_c) >> 5) && u.x0 > 0)
-                carry = ptx::ld_shared_f32_a(bnd_a + (uint32_t)((((cb - 1) & (kBndBlocks - 1)) * kBlk + (kBlk - 1)) * 4));
+            const long long t3 = kDbg ? clock64() : 0;
 #pragma unroll
             for (int i = 0; i < R; ++i) acc[i] = 0u;
             const uint32_t tile_a = ring_a + (uint32_t)slot * box_bytes;
@@ -377,7 +498,21 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
                 zero_below_diagonal_rows<R>(tile_a, lane, row0, col0, u.TR);
                 __syncwarp();
             }
-            systolic::sweep_block<R, true>(tile_a, lane_c, v, acc, carry, bnd_a + ring_slot, bnd_out_base + ring_slot, publisher);
+            if (col0 + kBlk > u.f_hi) {
+                // the band ends inside this box: nobody contracted the frames behind it, and whatever the
+                // ring holds there must at least be finite (f_hi is a multiple of 8: whole 16-byte groups)
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const int q = lane * R + i;
+                    if (q >= u.TR) continue;
+                    for (int cidx = (u.f_hi - col0) >> 2; cidx < 8; ++cidx)
+                        ptx::st_shared_v4_if(true, tile_a + (uint32_t)q * 128u + (uint32_t)((cidx ^ (q & 7)) << 4), make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+                __syncwarp();
+            }
+            systolic::sweep_block_ahead<R, 2, (R <= 3 ? 3 : 2)>(tile_a, lane_c, v, acc, carry, bnd_a + ring_slot, bnd_out_base + ring_slot,
+                                                               publishes && pub_lane, bar_out_base + (uint32_t)(cb & (kBndBlocks - 1)) * 8u);
+            const long long t4 = kDbg ? clock64() : 0;
 #pragma unroll
             for (int i = 0; i < R; ++i) acc[i] = __brev(acc[i]);
             if (on_diagonal) {
@@ -393,24 +528,33 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
                 if (lane * R + i < g.ring_rows) bits_p[i] = acc[i];
             bits_p += g.ring_rows;
             __syncwarp();                                   // every lane has read the box and the boundary slot
-            if (lane == 0) {
-                st_release_shared(ctl + kConsumed, cb - u.cb0 + 1);
-                zf.drip(zero_page, zf.per_block);
-            }
-            ptx::st_release_cluster_if(notifier && mirror_prev != 0u, mirror_prev, cb + 1);
-            ptx::st_release_cluster_if(notifier && mirror_next != 0u, mirror_next, cb + 1);
+            const long long t5 = kDbg ? clock64() : 0;
+            if (cb >= prev_first && cb <= prev_last) bnd_done(cb);
+            const long long t6 = kDbg ? clock64() : 0;
+            if (lane == 0) st_release_shared(ctl + kConsumed, cb - u.cb0 + 1);   // frees the box; the map builders read the bits after it
             if (++slot == g.NB) slot = 0;
+            if (kDbg) {
+                t_prev += t1 - t0;
+                t_credit += t2 - t1;
+                t_chunks += t3 - t2;
+                t_core += t4 - t3;
+                t_bits += t5 - t4;
+                t_done += t6 - t5;
+                t_fill += clock64() - t6;
+            }
         }
-        ptx::st_release_cluster_if(notifier && mirror_prev != 0u, mirror_prev, kDoneAll);
-        ptx::st_release_cluster_if(notifier && mirror_next != 0u, mirror_next, kDoneAll);
         // a NaN or an infinity anywhere in a token's history is still in its score now
 #pragma unroll
         for (int i = 0; i < R; ++i)
             if (lane * R + i < u.n_real && !(fabsf(v[i]) <= 3.402823466e38f)) nonfinite = 1;
     }
-    if (kDbg && dbg && lane == 0) dbg[4] = ptx::globaltimer_ns();
+    if (kDbg && dbg && lane == 0) {
+        dbg[4] = ptx::globaltimer_ns();
+        dbg[16] = t_chunks, dbg[17] = t_prev, dbg[18] = t_credit, dbg[19] = t_core;
+        dbg[20] = clock64() - t_begin, dbg[21] = u.cbend - u.cb0 + 1;
+        dbg[22] = t_bits, dbg[23] = t_done, dbg[24] = t_fill;
+    }
     if (lane == 0) {
-        zf.drip(zero_page, 0x7fffffff);
         if (zf.total > 0) {
             ptx::bulk_commit_group();
             ptx::bulk_wait_all();                          // the ones are written after the next barriers
@@ -421,6 +565,65 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
 }
 
 // ---------------------------------------------------------------------------------------------
+// backtrack (core.pyx:32-35), in parallel over 32-frame blocks
+//
+// The path sits on token x for frames (.., y]; the frame where it stepped onto x is the highest set
+// direction bit of x at or below y (mas_dp_cta.cuh: backtrack_tokens).  Inside one block that is a
+// short walk (the path descends a handful of tokens per 32 frames); what makes the whole backtrack
+// serial is only that a block's walk must know on which token the path LEAVES the block above.  So:
+//   * while the sweep is still running, the other warps tabulate for every finished block and every
+//     token of the slice "at the block's last frame on token x -> at the previous block's last
+//     frame on token x - m" (BLOCK MAP, one byte per token and block; 255 = the path leaves the slice
+//     inside the block);
+//   * after the sweep one thread per CTA composes the maps from its entry point downwards -- one
+//     dependent shared-memory load per block instead of a walk -- until the path leaves the slice,
+//     walks that one block to find the exact frame, and hands (token, frame) to the CTA below;
+//   * then one lane per block walks its block from the now known token and records for every token
+//     the frame where the path stepped onto it (`ylo`); a token's run ends one frame before the
+//     next token's begins.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLeft = 255;
+
+// The path is on local token xl at local frame y (0..31) of the block whose direction words are
+// `row` ([tokens of the slice]); col0 = the block's first frame, x0 = the slice's first token.
+// Returns the local token at the PREVIOUS block's last frame, -1 when the path leaves the slice
+// (then ylo[0] is the frame where it stepped onto the slice's first token).
+template <bool kSmem, bool kRecord>
+__device__ __forceinline__ int walk_block(const uint32_t *row, int xl, int y, int x0, int col0, int *ylo) {
+    while (xl >= 0 && x0 + xl > 0) {                        // token 0 is never left (core.pyx:34 `index != 0`)
+        const uint32_t w = (kSmem ? row[xl] : __ldcg(row + xl)) & (0xffffffffu >> (31 - y));
+        if (w == 0u) break;                                 // on this token since before the block
+        const int lo = 31 - __clz(w);                       // stepped onto it here
+        if (kRecord) ylo[xl] = col0 + lo;
+        --xl;
+        if (lo == 0) break;                                 // ... from the previous block's last frame
+        y = lo - 1;
+    }
+    return xl;
+}
+
+// Block maps of this CTA's slice for blocks cbl = first, first + step, ... as the sweep finishes them.
+template <bool kSmem>
+__device__ __forceinline__ void build_block_maps(const Geom &g, const Utt &u, const uint32_t *bits, unsigned char *maps, int *mapok,
+                                                 const int *ctl, int first, int step, int lane) {
+    const int nbox = u.cbend - u.cb0 + 1;
+    uint32_t spins = 0;
+    for (int cbl = first; cbl < nbox; cbl += step) {
+        while (ld_acquire_shared(ctl + kConsumed) <= cbl) {
+            __nanosleep(400);
+            if (++spins > kSpinLimit) systolic::spin_fail();
+        }
+        const uint32_t *row = bits + (size_t)(u.cb0 + cbl) * g.ring_rows;
+        for (int xl = lane; xl < u.n_real; xl += 32) {
+            const int r = walk_block<kSmem, false>(row, xl, 31, u.x0, 0, nullptr);
+            maps[(size_t)cbl * g.ring_rows + xl] = (unsigned char)(r < 0 ? kLeft : xl - r);
+        }
+        __syncwarp();
+        if (lane == 0) st_release_shared(mapok + cbl, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the literal redo of an utterance with non-finite scores (CTA 0 of the cluster, all its threads)
 // ---------------------------------------------------------------------------------------------
 static __device__ __forceinline__ void redo_utterance(const Geom &g, const Utt &u, const LogpParams &p, unsigned char *smem,
@@ -428,9 +631,18 @@ static __device__ __forceinline__ void redo_utterance(const Geom &g, const Utt &
     using namespace logp;
     const TileShape &t = g.t_ref;
     const int D = p.D, F = t.F, tx = u.tx, ty = u.ty;
+    // the contraction's operands as mas_logp_cta.cuh lays them out, with ONE frame buffer (nothing is
+    // prefetched here), then the exact sweep's two score columns
     float *sm = reinterpret_cast<float *>(smem + g.off_big);
-    const CtaSmem s = carve_smem(sm, D, t);
-    float *col = sm + cta_smem_floats(D, t);               // [2][tx], behind the contraction's operands
+    CtaSmem s;
+    s.sInv = sm;
+    s.sMiv = s.sInv + D * t.tile_rows;
+    s.sZ = s.sMiv + D * t.tile_rows;
+    s.sL1 = s.sZ + D * F;
+    s.sL4 = s.sL1 + t.tile_rows;
+    s.sL2 = s.sL4 + t.tile_rows;
+    s.sPart = s.sL2 + F;
+    float *col = s.sPart + 8 * t.tile_rows;                 // [2][tx]
     const systolic::Team team = systolic::whole_cta();
     const systolic::ExactBits eb{0u, bits, u.n_c, g.nblk};
     const int rts = ceil_div(tx, t.tile_rows);
@@ -461,7 +673,8 @@ static __device__ __forceinline__ void redo_utterance(const Geom &g, const Utt &
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int R, bool kDbg>
-__global__ void __launch_bounds__(kThreads, 1) mas_fused_kernel(PathParams pp, LogpParams lp, Geom g) {
+__global__ void __launch_bounds__(kThreads, 1)
+mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, LogpParams lp, Geom g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     // broadcast so that the compiler knows the warp index is warp-uniform (see dp_cta)
@@ -472,8 +685,12 @@ __global__ void __launch_bounds__(kThreads, 1) mas_fused_kernel(PathParams pp, L
     int *ctl = reinterpret_cast<int *>(smem + g.off_ctl);
     volatile int *vctl = ctl;
     float *bnd = reinterpret_cast<float *>(smem + g.off_bnd);
-    int2 *run = reinterpret_cast<int2 *>(smem + g.off_run);
+    int2 *run = reinterpret_cast<int2 *>(smem + g.off_run);       // redo path: [first frame, last frame] per token
+    int *ylo = reinterpret_cast<int *>(smem + g.off_run);         // frame where the path steps onto each token (+ one past the top)
+    int *xend = reinterpret_cast<int *>(smem + g.off_xend);       // token at the last frame of each block of the slice (-1: not composed)
+    int *mapok = xend + g.nblk;                                   // block map built?
     uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem + g.off_bits);
+    unsigned char *maps_s = smem + g.off_maps;
     const float neg = pp.max_neg_val;
 
     // FFMA role: every warp but the sweep warp, or only those on the other three schedulers
@@ -484,15 +701,28 @@ __global__ void __launch_bounds__(kThreads, 1) mas_fused_kernel(PathParams pp, L
     const int team = fw / g.team_warps, tn = g.team_warps * 32, ttid = fidx - team * tn;
     const bool in_team = is_ffma && team < g.nteams;
 
-    {   // once per CTA: the zero page, and what "advances" into token 0 after frame 0 (core.pyx:26-27)
+    uint64_t *zbars = reinterpret_cast<uint64_t *>(smem + g.off_bar);          // per team: full[kStages], empty[kStages]
+    uint64_t *bnd_bars = zbars + g.nteams * 2 * kStages;                       // [kBndBlocks]
+    {   // once per CTA: the zero page; what "advances" into token 0 after frame 0 (core.pyx:26-27) for
+        // CTA 0, finite values elsewhere (a slot may be read after the previous CTA's boundary token has
+        // left the band); the z pipelines' barriers
         float4 *zero4 = reinterpret_cast<float4 *>(smem + g.off_zero);
         for (int i = tid; i < kZeroPage / 16; i += kThreads) zero4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c == 0)
-            for (int i = tid; i < kBndBlocks * kBlk; i += kThreads) bnd[i] = neg;
+        for (int i = tid; i < kBndBlocks * kBlk; i += kThreads) bnd[i] = neg;
+        if (tid == 0) {
+            for (int t = 0; t < g.nteams; ++t)
+                for (int st = 0; st < kStages; ++st) {
+                    ptx::mbar_init(zbars + t * 2 * kStages + st, 1);
+                    ptx::mbar_init(zbars + t * 2 * kStages + kStages + st, (uint32_t)g.team_warps);
+                }
+            ptx::fence_barrier_init();
+            ptx::prefetch_tensormap(&tmap_z);
+        }
         ptx::fence_proxy_async();
         __syncthreads();
     }
-    long long *dbg = (kDbg && pp.dbg_cycles) ? pp.dbg_cycles + (size_t)blockIdx.x * 16 : nullptr;
+    long long *dbg = (kDbg && pp.dbg_cycles) ? pp.dbg_cycles + (size_t)blockIdx.x * 32 : nullptr;
+    int zseq = 0;                       // z panels this thread's team has consumed so far (mbarrier phases run on)
 
     for (int it = 0;; ++it) {
         // static, serpentine: batches come sorted by length (dataset.py:79-81), so consecutive rounds
@@ -515,20 +745,36 @@ __global__ void __launch_bounds__(kThreads, 1) mas_fused_kernel(PathParams pp, L
         u.CG = max(1, min(tn / u.RG, g.CG_cap));
         u.F = 8 * u.CG;
         u.cb0 = u.x0 >> 5;
-        u.cbend = u.n_real > 0 ? min(u.ty - 1, u.x0 + u.n_real - 1 + (u.ty - u.tx)) >> 5 : u.cb0 - 1;
-        u.nch = ceil_div((u.cbend - u.cb0 + 1) * kBlk, u.F);
+        {
+            // the slice is in the band from frame x0 (core.pyx:18: x <= y) to where its last token leaves it
+            const int y_last = min(u.ty - 1, u.x0 + u.n_real - 1 + (u.ty - u.tx));
+            u.cbend = u.n_real > 0 ? y_last >> 5 : u.cb0 - 1;
+            u.f_lo = u.x0 & ~7;
+            u.f_hi = u.n_real > 0 ? min((y_last + 8) & ~7, (u.cbend + 1) * kBlk) : u.f_lo;
+            u.nch = ceil_div(u.f_hi - u.f_lo, u.F);
+        }
         const bool active = u.n_real > 0;
 
         if (tid == 0) {
             for (int i = 0; i < kMaxTeams; ++i) ctl[kTeamDone + i] = 0;
             ctl[kConsumed] = 0;
-            ctl[kDonePrev] = (c == 0) ? kDoneAll : -1;
-            if (c == K - 1) ctl[kDoneNext] = kDoneAll;
-            ctl[kBtFlag] = 0;
+            ctl[kCredit] = max(u.cb0, ((u.x0 + u.n_c) >> 5) - 1);     // = the first block this sweep publishes
             ctl[kRedo] = 0;
-            if (c > 0)   // tell the previous CTA where its consumer (this sweep) starts
-                ptx::st_cluster_u32(ptx::mapa(ptx::smem_u32(ctl + kDoneNext), (uint32_t)(c - 1)), (uint32_t)(active ? u.cb0 - 1 : kDoneAll));
+            // the boundary ring's barriers start every utterance afresh; a consuming sweep arms them all
+            for (int i = 0; i < kBndBlocks; ++i) {
+                if (it > 0) ptx::mbar_inval(bnd_bars + i);
+                ptx::mbar_init(bnd_bars + i, 1);
+            }
+            ptx::fence_barrier_init();
+            if (c > 0 && active)
+                for (int i = 0; i < kBndBlocks; ++i) ptx::mbar_arrive_expect_tx(bnd_bars + i, kBlk * 4);
+            // the backtrack's hand-over from the CTA above: 8 bytes (token, frame)
+            if (it > 0) ptx::mbar_inval(bnd_bars + kBndBlocks);
+            ptx::mbar_init(bnd_bars + kBndBlocks, 1);
+            ptx::fence_barrier_init();
+            ptx::mbar_arrive_expect_tx(bnd_bars + kBndBlocks, 8);
         }
+        for (int i = tid; i <= u.cbend - u.cb0; i += kThreads) xend[i] = -1, mapok[i] = 0;
         if (kDbg && dbg && tid == 0) dbg[0] = ptx::globaltimer_ns();
         ptx::cluster_sync();
 
@@ -543,13 +789,24 @@ __global__ void __launch_bounds__(kThreads, 1) mas_fused_kernel(PathParams pp, L
             uint32_t *bits_g = g.bits_in_smem ? nullptr : g.ws_bits + ((size_t)cluster_id * K + c) * g.nblk * g.ring_rows;
             nonfinite = sweep_slice<R, kDbg>(g, u, smem, ctl, neg, zf, bits_g, dbg);
         } else if (in_team && active) {
-            stage_ops(g, u, lp, smem, fidx, g.nteams * tn);
+            team_contract<false>(tmap_z, g, u, lp, smem, ctl, team, ttid, tn, zseq, true);
+            stage_ops(g, u, lp, smem, fidx, g.nteams * tn, kDbg ? dbg : nullptr);
             if (kDbg && dbg && fidx == 0) dbg[1] = ptx::globaltimer_ns();
             if (lp.x_logs == nullptr)
-                team_contract<true>(g, u, lp, smem, ctl, team, ttid, tn);
+                zseq = team_contract<true>(tmap_z, g, u, lp, smem, ctl, team, ttid, tn, zseq, false);
             else
-                team_contract<false>(g, u, lp, smem, ctl, team, ttid, tn);
+                zseq = team_contract<false>(tmap_z, g, u, lp, smem, ctl, team, ttid, tn, zseq, false);
             if (kDbg && dbg && ttid == 0) dbg[8 + team] = ptx::globaltimer_ns();
+        }
+        uint32_t *const bits_w = g.bits_in_smem ? nullptr : g.ws_bits + ((size_t)cluster_id * K + c) * g.nblk * g.ring_rows;
+        unsigned char *const maps = g.bits_in_smem ? maps_s : g.ws_maps + ((size_t)cluster_id * K + c) * g.nblk * g.ring_rows;
+        if ((warp & 3) != 0 && active) {
+            // the warps on the other three schedulers, once their contraction is done: the backtrack's block maps
+            const int bw = (warp - 1) - (warp >> 2);
+            if (g.bits_in_smem)
+                build_block_maps<true>(g, u, bits_s, maps, mapok, ctl, bw, 12, lane);
+            else
+                build_block_maps<false>(g, u, bits_w, maps, mapok, ctl, bw, 12, lane);
         }
         if (!g.bits_in_smem) __threadfence();
 
@@ -573,46 +830,109 @@ __global__ void __launch_bounds__(kThreads, 1) mas_fused_kernel(PathParams pp, L
         }
         if (kDbg && dbg && tid == 0) dbg[5] = ptx::globaltimer_ns();
 
-        // ---- backtrack (core.pyx:32-35) by TOKENS, handed down from CTA to CTA ----
+        // ---- backtrack (core.pyx:32-35), handed down from CTA to CTA ----
         const int c_last = (u.tx > 0) ? (u.tx - 1) / u.n_c : -1;   // CTA that owns the last token
-        if (tid == 0 && c <= c_last) {
-            int x, y_hi;
-            if (c == c_last) {
-                x = u.tx - 1;
-                y_hi = u.ty - 1;
-            } else {
-                uint32_t spins = 0;
-                while (ptx::ld_acquire_cluster_shared(ctl + kBtFlag) == 0)
-                    if (++spins > kSpinLimit) systolic::spin_fail();
-                x = vctl[kBtToken];
-                y_hi = vctl[kBtFrame];
-            }
-            const int x_min = max(u.x0, 1);
-            if (x >= x_min)
-                y_hi = (bits_gl == nullptr) ? systolic::backtrack_tokens<true>(bits_s, bits_rows, u.x0, x, y_hi, x_min, run)
-                                            : systolic::backtrack_tokens<false>(bits_gl, bits_rows, u.x0, x, y_hi, x_min, run);
-            if (c == 0) {
-                run[0] = make_int2(0, y_hi);
-            } else {
-                const uint32_t peer = ptx::mapa(ptx::smem_u32(ctl + kBtFlag), (uint32_t)(c - 1));
-                ptx::st_cluster_u32(peer + 4, (uint32_t)(u.x0 - 1));
-                ptx::st_cluster_u32(peer + 8, (uint32_t)y_hi);
-                ptx::st_release_cluster_if(true, peer, 1);
-            }
-        }
-        __syncthreads();
-        if (kDbg && dbg && tid == 0) dbg[6] = ptx::globaltimer_ns();
-
-        // ---- dense path: ones, durations, frame -> token ----
+        const uint32_t bt_bar_a = ptx::smem_u32(bnd_bars + kBndBlocks);
         float *out = pp.path + (int64_t)b * T_x * T_y;
-        for (int xl = tid; xl < u.n_real; xl += kThreads) {
-            const int x = u.x0 + xl;
-            const int2 r = run[xl];
-            float *row = out + (int64_t)x * T_y;
-            for (int y = r.x; y <= r.y; ++y) row[y] = 1.f;
-            if (pp.frame_token)
-                for (int y = r.x; y <= r.y; ++y) pp.frame_token[(int64_t)b * T_y + y] = x;
-            if (pp.durations) pp.durations[(int64_t)b * T_x + x] = r.y - r.x + 1;
+        if (redo) {
+            // (rare) the redo's direction words are in global memory, tokens strided by the slice: the
+            // serial token walk of kernel (1)
+            if (tid == 0 && c <= c_last) {
+                int x, y_hi;
+                if (c == c_last) {
+                    x = u.tx - 1;
+                    y_hi = u.ty - 1;
+                } else {
+                    uint32_t spins = 0;
+                    while (!ptx::mbar_try_wait_a(bt_bar_a, 0u))
+                        if (++spins > kSpinLimit) systolic::spin_fail();
+                    x = vctl[kBtToken];
+                    y_hi = vctl[kBtFrame];
+                }
+                const int x_min = max(u.x0, 1);
+                if (x >= x_min) y_hi = systolic::backtrack_tokens<false>(bits_gl, bits_rows, u.x0, x, y_hi, x_min, run);
+                if (c == 0) {
+                    run[0] = make_int2(0, y_hi);
+                } else {
+                    const uint32_t peer = ptx::mapa(ptx::smem_u32(ctl + kBtToken), (uint32_t)(c - 1));   // (8-byte aligned)
+                    ptx::st_async_b64(peer, (uint64_t)(uint32_t)(u.x0 - 1) | ((uint64_t)(uint32_t)y_hi << 32),
+                                      ptx::mapa(bt_bar_a, (uint32_t)(c - 1)));
+                }
+            }
+            __syncthreads();
+            for (int xl = tid; xl < u.n_real; xl += kThreads) {
+                const int x = u.x0 + xl;
+                const int2 r = run[xl];
+                float *row = out + (int64_t)x * T_y;
+                for (int y = r.x; y <= r.y; ++y) row[y] = 1.f;
+                if (pp.frame_token)
+                    for (int y = r.x; y <= r.y; ++y) pp.frame_token[(int64_t)b * T_y + y] = x;
+                if (pp.durations) pp.durations[(int64_t)b * T_x + x] = r.y - r.x + 1;
+            }
+        } else {
+            const uint32_t *bits_b = g.bits_in_smem ? bits_s : bits_w;
+            if (tid == 0 && c <= c_last) {
+                // compose the block maps from the entry point down; walk only the entry and the exit block
+                int xl, y;
+                if (c == c_last) {
+                    xl = u.tx - 1 - u.x0;
+                    y = u.ty - 1;
+                } else {
+                    uint32_t spins = 0;
+                    while (!ptx::mbar_try_wait_a(bt_bar_a, 0u))
+                        if (++spins > kSpinLimit) systolic::spin_fail();
+                    xl = vctl[kBtToken] - u.x0;
+                    y = vctl[kBtFrame];
+                }
+                ylo[xl + 1] = y + 1;                        // where the token above begins
+                int cb = y >> 5;
+                const uint32_t *row = bits_b + (size_t)cb * g.ring_rows;
+                xl = g.bits_in_smem ? walk_block<true, true>(row, xl, y & 31, u.x0, cb * kBlk, ylo)
+                                    : walk_block<false, true>(row, xl, y & 31, u.x0, cb * kBlk, ylo);
+                while (xl >= 0 && --cb >= u.cb0) {
+                    const int m = ld_acquire_shared(mapok + (cb - u.cb0)) ? maps[(size_t)(cb - u.cb0) * g.ring_rows + xl] : kLeft;
+                    if (m == kLeft) {                       // the path leaves the slice here (or nobody built this block's map)
+                        row = bits_b + (size_t)cb * g.ring_rows;
+                        xl = g.bits_in_smem ? walk_block<true, true>(row, xl, 31, u.x0, cb * kBlk, ylo)
+                                            : walk_block<false, true>(row, xl, 31, u.x0, cb * kBlk, ylo);
+                        continue;
+                    }
+                    xend[cb - u.cb0] = xl;
+                    xl -= m;
+                }
+                if (c == 0) {
+                    ylo[0] = 0;
+                } else {
+                    ptx::st_async_b64(ptx::mapa(ptx::smem_u32(ctl + kBtToken), (uint32_t)(c - 1)),
+                                      (uint64_t)(uint32_t)(u.x0 - 1) | ((uint64_t)(uint32_t)(ylo[0] - 1) << 32),
+                                      ptx::mapa(bt_bar_a, (uint32_t)(c - 1)));
+                }
+            }
+            __syncthreads();
+            if (kDbg && dbg && tid == 0) dbg[6] = ptx::globaltimer_ns();
+            // one lane per composed block: the frames where the path steps onto the tokens it visits there
+            if (warp < 4 && c <= c_last) {
+                for (int cbl = tid; cbl <= u.cbend - u.cb0; cbl += 128) {
+                    const int xe = xend[cbl];
+                    if (xe < 0) continue;
+                    const uint32_t *row = bits_b + (size_t)(u.cb0 + cbl) * g.ring_rows;
+                    if (g.bits_in_smem)
+                        walk_block<true, true>(row, xe, 31, u.x0, (u.cb0 + cbl) * kBlk, ylo);
+                    else
+                        walk_block<false, true>(row, xe, 31, u.x0, (u.cb0 + cbl) * kBlk, ylo);
+                }
+            }
+            __syncthreads();
+            // ---- dense path: ones, durations, frame -> token ----
+            for (int xl = tid; xl < u.n_real; xl += kThreads) {
+                const int x = u.x0 + xl;
+                const int y0 = ylo[xl], y1 = ylo[xl + 1];
+                float *row = out + (int64_t)x * T_y;
+                for (int y = y0; y < y1; ++y) row[y] = 1.f;
+                if (pp.frame_token)
+                    for (int y = y0; y < y1; ++y) pp.frame_token[(int64_t)b * T_y + y] = x;
+                if (pp.durations) pp.durations[(int64_t)b * T_x + x] = y1 - y0;
+            }
         }
         if (pp.durations)
             for (int x = u.tx + c * kThreads + tid; x < T_x; x += K * kThreads) pp.durations[(int64_t)b * T_x + x] = 0;
@@ -635,23 +955,76 @@ static int tokens_per_lane(int T_x, int K) {
 }
 
 // Shared-memory layout and team shape for K CTAs per utterance; false when it does not fit.
-static bool make_geom(int D, int T_x, int T_y, int K, int ffma_all, int teams_forced, int max_smem, Geom &g) {
-    g = Geom{};
+// (the contraction's frames per utterance, for the estimates: the band of a full-length slice)
+static int slice_frames(int T_x, int T_y, int max_slice) { return (T_y > T_x ? T_y - T_x : 0) + max_slice + 8; }
+
+static bool layout_geom(int D, int T_x, int max_smem, Geom &g) {
+    int off = 0;
+    g.off_zero = off, off += kZeroPage;
+    g.off_bnd = off, off += kBndBlocks * kBlk * 4;
+    g.off_run = off, off += (g.ring_rows + 2) * 8;
+    g.off_xend = off, off += 2 * g.nblk * 4;               // + the "block map built" flags
+    off = (int)align_up((size_t)off, 16);
+    g.off_ctl = off, off += kCtlInts * 4;
+    g.off_bar = off, off += (g.nteams * 2 * kStages + kBndBlocks + 1) * 8;
+    off = (int)align_up((size_t)off, 1024);
+    g.off_big = off;
+    g.off_ops = off, off += 2 * D * g.tr_max * 4;
+    g.off_l14 = off, off += 2 * g.tr_max * 4;
+    g.off_part = off, off += 8 * g.tr_max * 4;
+    off = (int)align_up((size_t)off, 128);
+    g.off_z = off, off += g.nteams * kStages * kChan * g.F_cap * 4;   // TMA destinations: 128-byte aligned (F_cap is even)
+    g.off_l2 = off, off += g.nteams * g.F_cap * 4;
+    off = (int)align_up((size_t)off, 1024);
+    g.off_ring = off;
+    const int box = g.ring_rows * 128;
+    // the ring must hold the chunk being stored and the box being swept; with every team's chunk in
+    // flight it never stalls them; stage_ops parks the raw token-side values in it (2 arrays at least)
+    int nb_floor = ceil_div(g.F_cap + 2 * kBlk, kBlk);
+    if (nb_floor * box < 2 * D * g.tr_max * 4) nb_floor = ceil_div(2 * D * g.tr_max * 4, box);
+    const int bits_bytes = g.nblk * g.ring_rows * 5;       // direction words + one map byte per token and block
+    const int redo_need = g.off_big + (logp::cta_smem_floats(D, g.t_ref) - D * g.t_ref.F) * 4 + 2 * T_x * 4 + 16;   // (redo_utterance)
+    if (redo_need > max_smem) return false;
+    for (int bits_smem = 1; bits_smem >= 0; --bits_smem) {
+        const int left = max_smem - g.off_ring - (bits_smem ? bits_bytes : 0);
+        int nb = left / box;
+        if (nb > 32) nb = 32;
+        // the direction bits leave shared memory before the ring gets too shallow for the teams
+        if (nb >= (bits_smem ? ceil_div((g.nteams + 1) * g.F_cap + 2 * kBlk, kBlk) : nb_floor)) {
+            g.NB = nb;
+            g.bits_in_smem = bits_smem;
+            g.ops_tmp3 = (int64_t)nb * box >= (int64_t)3 * D * g.tr_max * 4;
+            g.off_bits = g.off_ring + nb * box;
+            g.off_maps = g.off_bits + g.nblk * g.ring_rows * 4;
+            g.total = g.off_bits + (bits_smem ? bits_bytes : 0);
+            if (g.total < redo_need) g.total = redo_need;
+            return true;
+        }
+    }
+    return false;
+}
+
+// Shared-memory layout and team shape for K CTAs per utterance; false when nothing fits.
+// Teams: a pass (every thread contracts its 4 x 8 cells over all channels) takes the same time
+// whatever the team shape, so the shape that needs the fewest passes for a full-length utterance
+// wins; among those, more teams (narrower chunks: the sweep starts earlier and trails less).
+static bool make_geom(int D, int T_x, int T_y, int K, int ffma_all, int teams_forced, int max_smem, Geom &best) {
+    Geom g0{};
     const int R = tokens_per_lane(T_x, K);
     if (R > 8) return false;
-    g.K = K;
-    g.ffma_all = ffma_all;
-    g.max_slice = ceil_div(ceil_div(T_x, K), R) * R;
-    g.tr_max = ceil_div(g.max_slice, kGemmTM) * kGemmTM;
-    g.ring_rows = ceil_div(g.tr_max, 8) * 8;
-    g.nblk = ceil_div(T_y, kBlk);
-    g.t_ref = make_tile_shape(T_x, T_y);
-    g.nsh = kGemmThreads / g.t_ref.tile_rows;
-    g.nsh = g.nsh < 1 ? 1 : (g.nsh > 4 ? 4 : g.nsh);
-    g.dsh = ceil_div(D, g.nsh);
-    const int RG = g.tr_max / kGemmTM, warps = ffma_all ? 15 : 12;
-    // teams: as many as keep the threads busy (finer chunks: the sweep starts earlier and trails less)
-    double best = -1.0;
+    g0.K = K;
+    g0.ffma_all = ffma_all;
+    g0.max_slice = ceil_div(ceil_div(T_x, K), R) * R;
+    g0.tr_max = ceil_div(g0.max_slice, kGemmTM) * kGemmTM;
+    g0.ring_rows = ceil_div(g0.tr_max, 8) * 8;
+    g0.nblk = ceil_div(T_y, kBlk);
+    g0.t_ref = make_tile_shape(T_x, T_y);
+    g0.nsh = kGemmThreads / g0.t_ref.tile_rows;
+    g0.nsh = g0.nsh < 1 ? 1 : (g0.nsh > 4 ? 4 : g0.nsh);
+    g0.dsh = ceil_div(D, g0.nsh);
+    const int RG = g0.tr_max / kGemmTM, warps = ffma_all ? 15 : 12;
+    const int frames = slice_frames(T_x, T_y, g0.max_slice);
+    int best_passes = -1;
     for (int nt = 1; nt <= 5; ++nt) {
         if (warps % nt) continue;
         if (teams_forced > 0 && nt != teams_forced) continue;
@@ -660,50 +1033,19 @@ static bool make_geom(int D, int T_x, int T_y, int K, int ffma_all, int teams_fo
         cg = cg > 32 ? 32 : cg;
         cg = cg > tn / 8 ? tn / 8 : cg;
         if (cg < 4) continue;
-        const double score = (double)(RG * cg * nt) / (warps * 32) * (1.0 + 0.02 * nt);
-        if (score > best) {
-            best = score;
-            g.nteams = nt;
-            g.team_warps = tw;
-            g.CG_cap = cg;
+        Geom g = g0;
+        g.nteams = nt;
+        g.team_warps = tw;
+        g.CG_cap = cg;
+        g.F_cap = 8 * cg;
+        if (!layout_geom(D, T_x, max_smem, g)) continue;
+        g.passes = ceil_div(frames, nt * g.F_cap);
+        if (best_passes < 0 || g.passes <= best_passes) {
+            best_passes = g.passes;
+            best = g;
         }
     }
-    if (best < 0) return false;
-    g.F_cap = 8 * g.CG_cap;
-
-    int off = 0;
-    g.off_zero = off, off += kZeroPage;
-    g.off_bnd = off, off += kBndBlocks * kBlk * 4;
-    g.off_run = off, off += g.ring_rows * 8;
-    g.off_ctl = off, off += kCtlInts * 4;
-    off = (int)align_up((size_t)off, 1024);
-    g.off_big = off;
-    g.off_ops = off, off += 2 * D * g.tr_max * 4;
-    g.off_l14 = off, off += 2 * g.tr_max * 4;
-    g.off_part = off, off += 8 * g.tr_max * 4;
-    g.off_z = off, off += g.nteams * 2 * kChan * g.F_cap * 4;
-    g.off_l2 = off, off += g.nteams * g.F_cap * 4;
-    off = (int)align_up((size_t)off, 1024);
-    g.off_ring = off;
-    const int box = g.ring_rows * 128;
-    const int nb_min = ceil_div((g.nteams + 1) * g.F_cap + kBlk, kBlk);
-    const int bits_bytes = g.nblk * g.ring_rows * 4;
-    const int redo_need = g.off_big + logp::cta_smem_floats(D, g.t_ref) * 4 + 2 * T_x * 4 + 16;
-    if (redo_need > max_smem) return false;
-    for (int bits_smem = 1; bits_smem >= 0; --bits_smem) {
-        const int left = max_smem - g.off_ring - (bits_smem ? bits_bytes : 0);
-        int nb = left / box;
-        if (nb > 32) nb = 32;
-        if (nb >= nb_min) {
-            g.NB = nb;
-            g.bits_in_smem = bits_smem;
-            g.off_bits = g.off_ring + nb * box;
-            g.total = g.off_bits + (bits_smem ? bits_bytes : 0);
-            if (g.total < redo_need) g.total = redo_need;
-            return true;
-        }
-    }
-    return false;
+    return best_passes >= 0;
 }
 
 static size_t redo_scratch_bytes(int slots, int T_x, int T_y) {
@@ -715,9 +1057,10 @@ static size_t ws_bits_bytes(int slots, int T_x, int T_y) {
     // [clusters][K][nblk][ring_rows]: K x ring_rows <= T_x + K x (R + 4 + 8) rounding
     return align_up((size_t)slots * ceil_div(T_y, kBlk) * (T_x + 160) * 4, 256);
 }
+static size_t ws_maps_bytes(int slots, int T_x, int T_y) { return align_up((size_t)slots * ceil_div(T_y, kBlk) * (T_x + 160), 256); }
 
 template <int R>
-static int launch_r(const PathParams &pp, const LogpParams &lp, Geom &g, int B, int dev, cudaStream_t stream) {
+static int launch_r(const CUtensorMap &tmap_z, const PathParams &pp, const LogpParams &lp, Geom &g, int B, int dev, cudaStream_t stream) {
     static SmemOptIn optin[2];
     const bool dbgk = pp.dbg_cycles != nullptr;
     auto kern = dbgk ? mas_fused_kernel<R, true> : mas_fused_kernel<R, false>;
@@ -745,8 +1088,30 @@ static int launch_r(const PathParams &pp, const LogpParams &lp, Geom &g, int B, 
     if (nc > kMaxClusters) nc = kMaxClusters;
     g.NC = B < nc ? B : nc;
     cfg.gridDim = dim3((unsigned)(g.NC * g.K));
-    MAS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, pp, lp, g));
+    MAS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmap_z, pp, lp, g));
     return MAS_OK;
+}
+
+// What the launch costs, from the timelines measured on B200 (profiles/r2_fused_timeline.txt): per
+// round of resident clusters ~18.4 us per contraction pass, ~25 us of start, sweep tail and output,
+// ~4 us per CTA the sweep's chain and the backtrack hop through; direction bits and block maps in
+// the workspace (long slices) cost ~3 us per 32-frame block of L2 round trips.
+static double estimate_us(const Geom &g, int B, int num_sms) {
+    const int nc = num_sms / g.K < 1 ? 1 : num_sms / g.K;
+    const int rounds = ceil_div(B, nc);
+    const int slice_blocks = ceil_div(g.passes * g.nteams * g.F_cap, kBlk);
+    return rounds * (g.passes * 18.4 + 25.0 + 4.0 * g.K + (g.bits_in_smem ? 0.0 : 3.0 * slice_blocks));
+}
+// ... and the two kernels back to back: the materialising kernel's rounds of (token tile, chunk)
+// units (16.5 us each on every SM, mas_logp.cu) + kernel (1) (latency floor 41 ns per frame, else
+// ~500 Gcells/s).
+static double estimate_two_kernels_us(int B, int T_x, int T_y) {
+    const TileShape t = make_tile_shape(T_x, T_y);
+    const double units = (double)B * t.row_tiles * t.nchunks;
+    const double logp_us = ceil(units / 148.0) * 16.5 + 6.0;
+    const double cells = (double)B * T_x * T_y;
+    const double k1 = cells / 0.5e6 > 0.041 * T_y ? cells / 0.5e6 : 0.041 * T_y;
+    return logp_us + k1 + 5.0;
 }
 
 // The geometry for `num_sms` SMs with `max_smem` bytes of opt-in shared memory per CTA.
@@ -764,8 +1129,7 @@ static bool choose_geom(int B, int D, int T_x, int T_y, int max_smem, int num_sm
         if (!make_geom(D, T_x, T_y, K, ffma_all, teams_forced, max_smem, g)) continue;
         const int nc = num_sms / K;
         if (nc < 1) continue;
-        const int rounds = ceil_div(B, nc);
-        const double cost = rounds * (1.0 / K + 0.04);              // a slice's share of the work + what a cluster costs
+        const double cost = estimate_us(g, B, num_sms);
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best = g;
@@ -782,7 +1146,8 @@ size_t fused_workspace_bytes(int B, int D, int T_x, int T_y) {
     (void)D;
     using namespace fused;
     const int slots = B < kMaxClusters ? B : kMaxClusters;
-    return redo_scratch_bytes(slots, T_x, T_y) + redo_bits_bytes(slots, T_x, T_y) + ws_bits_bytes(slots, T_x, T_y);
+    return redo_scratch_bytes(slots, T_x, T_y) + redo_bits_bytes(slots, T_x, T_y) + ws_bits_bytes(slots, T_x, T_y) +
+           ws_maps_bytes(slots, T_x, T_y);
 }
 
 // Host-only: the geometry the launcher picks.
@@ -799,7 +1164,7 @@ bool debug_fused_geom(int B, int D, int T_x, int T_y, int max_smem, int num_sms,
 // MAS_OK: launched.  MAS_ERR_UNSUPPORTED_SHAPE: not for the single launch (the caller runs the two
 // kernels back to back instead).
 int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y_len, float *path, int32_t *durations,
-                 int32_t *frame_token, void *workspace, size_t workspace_bytes, float max_neg_val, cudaStream_t stream) {
+                 int32_t *frame_token, void *workspace, size_t workspace_bytes, float max_neg_val, bool force, cudaStream_t stream) {
     using namespace fused;
     static const bool debug = getenv("MAS_B200_DEBUG") != nullptr;
 #define MAS_FUSED_NO(why) do { if (debug) fprintf(stderr, "[mas_b200] single launch not taken: %s\n", why); return MAS_ERR_UNSUPPORTED_SHAPE; } while (0)
@@ -816,6 +1181,12 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
     if (int rc = get_device_info(dev, di)) return rc;
     Geom g;
     if (!choose_geom(B, D, T_x, T_y, di.max_smem_optin - 1024, di.num_sms, g)) MAS_FUSED_NO("no slice geometry fits shared memory");
+    static const char *mode_env = getenv("MAS_B200_FUSED_MODE");    // "cluster": always the single launch (experiments)
+    if (!force && !(mode_env && mode_env[0] == 'c')) {
+        const double one = estimate_us(g, B, di.num_sms), two = estimate_two_kernels_us(B, T_x, T_y);
+        if (debug) fprintf(stderr, "[mas_b200] estimates: single launch %.0f us, two kernels %.0f us\n", one, two);
+        if (two < one) MAS_FUSED_NO("the two kernels are estimated faster for this shape");
+    }
 
     const int slots = B < kMaxClusters ? B : kMaxClusters;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
@@ -824,6 +1195,8 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
     g.redo_bits = reinterpret_cast<uint32_t *>(ws);
     ws += redo_bits_bytes(slots, T_x, T_y);
     g.ws_bits = reinterpret_cast<uint32_t *>(ws);
+    ws += ws_bits_bytes(slots, T_x, T_y);
+    g.ws_maps = ws;
 
     LogpParams lp = lp_in;
     lp.logp = nullptr;
@@ -841,18 +1214,33 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
     pp.max_neg_val = max_neg_val;
     pp.dbg_cycles = g_dbg_cycles.load();
 
+    // z [B][D][T_y] for the teams' panel loads: boxes of [kChan channels x F frames]; channels and frames
+    // out of range arrive as zeros
+    PFN_cuTensorMapEncodeTiled_v12000 encode = systolic::get_encode_fn();
+    if (encode == nullptr) MAS_FUSED_NO("no cuTensorMapEncodeTiled");
+    CUtensorMap tmap_z;
+    {
+        const cuuint64_t gdim[3] = {(cuuint64_t)T_y, (cuuint64_t)D, (cuuint64_t)B};
+        const cuuint64_t gstride[2] = {(cuuint64_t)T_y * 4, (cuuint64_t)D * T_y * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)g.F_cap, (cuuint32_t)kChan, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult cr = encode(&tmap_z, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(lp_in.z), gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) MAS_FUSED_NO("tensor map encode failed");
+    }
     const int R = tokens_per_lane(T_x, g.K);
     if (debug)
         fprintf(stderr, "[mas_b200] single launch: clusters of %d CTAs, slices of <= %d tokens (R=%d), %d FFMA warps in %d teams, chunks of <= %d frames, ring of %d boxes x %d rows, bits %s, %d B smem\n",
                 g.K, g.max_slice, R, g.ffma_all ? 15 : 12, g.nteams, g.F_cap, g.NB, g.ring_rows, g.bits_in_smem ? "in smem" : "in workspace", g.total);
     switch (R) {
-        case 1: return launch_r<1>(pp, lp, g, B, dev, stream);
-        case 2: return launch_r<2>(pp, lp, g, B, dev, stream);
-        case 3: return launch_r<3>(pp, lp, g, B, dev, stream);
-        case 4: return launch_r<4>(pp, lp, g, B, dev, stream);
-        case 5: return launch_r<5>(pp, lp, g, B, dev, stream);
-        case 6: return launch_r<6>(pp, lp, g, B, dev, stream);
-        case 8: return launch_r<8>(pp, lp, g, B, dev, stream);
+        case 1: return launch_r<1>(tmap_z, pp, lp, g, B, dev, stream);
+        case 2: return launch_r<2>(tmap_z, pp, lp, g, B, dev, stream);
+        case 3: return launch_r<3>(tmap_z, pp, lp, g, B, dev, stream);
+        case 4: return launch_r<4>(tmap_z, pp, lp, g, B, dev, stream);
+        case 5: return launch_r<5>(tmap_z, pp, lp, g, B, dev, stream);
+        case 6: return launch_r<6>(tmap_z, pp, lp, g, B, dev, stream);
+        case 8: return launch_r<8>(tmap_z, pp, lp, g, B, dev, stream);
         default: return MAS_ERR_UNSUPPORTED_SHAPE;
     }
 }

@@ -93,6 +93,6 @@ int launch_logp(const LogpParams &p, cudaStream_t stream);
 size_t fused_workspace_bytes(int B, int D, int T_x, int T_y);
 bool debug_fused_geom(int B, int D, int T_x, int T_y, int max_smem, int num_sms, int32_t *out12);   // host only
 int launch_fused(const LogpParams &lp, const int32_t *x_len, const int32_t *y_len, float *path, int32_t *durations,
-                 int32_t *frame_token, void *workspace, size_t workspace_bytes, float max_neg_val, cudaStream_t stream);
+                 int32_t *frame_token, void *workspace, size_t workspace_bytes, float max_neg_val, bool force, cudaStream_t stream);
 
 }  // namespace mas

@@ -71,6 +71,9 @@ __device__ __forceinline__ float ld_shared_f32_a(uint32_t addr) {
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_inval(uint64_t *bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // make barrier initialisation visible to the async (TMA) proxy and to other threads
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -81,6 +84,12 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // non-blocking probe of a phase
 __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
@@ -105,6 +114,16 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         " [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(uint32_t smem_dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void red_release_shared_add(int *p, int v) {
+    asm volatile("red.release.cta.shared::cta.add.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_shared_if(bool pred, int *p, int v) {
     asm volatile(
@@ -134,6 +153,9 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src
     // src-size 0 zero-fills the destination (out-of-range frames)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(valid ? 16 : 0)
                  : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -167,6 +189,21 @@ __device__ __forceinline__ void st_cluster_v4_if(bool pred, uint32_t addr, float
         "}\n"
         ::"r"((uint32_t)pred), "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
         : "memory");
+}
+// remote 16-byte store that completes 16 bytes of a transaction count on an mbarrier of the same
+// remote CTA (both shared::cluster addresses): data and signal travel together, nobody fences
+__device__ __forceinline__ void st_async_v4_if(bool pred, uint32_t addr, float4 v, uint32_t mbar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %0, 0;\n"
+        "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%1], {%2, %3, %4, %5}, [%6];\n"
+        "}\n"
+        ::"r"((uint32_t)pred), "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(mbar)
+        : "memory");
+}
+__device__ __forceinline__ void st_async_b64(uint32_t addr, uint64_t v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(addr), "l"(v), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
     float4 v;

@@ -60,9 +60,11 @@ void mas_b200_debug_set_cycle_buffer(void *device_buffer);
 /* Testing hook: force the number of CTAs (thread-block cluster size: 1, 2, 4, 8) that share one
  * utterance in kernel (1); 0 restores the heuristic. */
 void mas_b200_debug_force_cluster(int ctas_per_utterance);
-/* Testing hook: non-zero makes mas_b200_fused_maximum_path_f32 run its two programs as two launches
- * (the path it takes anyway for shapes the single launch does not support). */
-void mas_b200_debug_force_unfused(int on);
+/* Testing hook for mas_b200_fused_maximum_path_f32: 0 = the entry chooses between its single launch
+ * (a cluster of CTAs per utterance, scores never leave shared memory) and the two kernels back to
+ * back by its cost estimate for the shape; 1 = always the two kernels; 2 = the single launch
+ * whenever the shape allows it. */
+void mas_b200_debug_force_unfused(int mode);
 /* Testing hooks, HOST only (no device needed): how the contraction's work is laid out.
  *   debug_tile_shape: out6 = {row_tiles, tile_rows, row groups, column groups, frames per chunk, chunks}
  *   debug_deal: the deal of (row, chunk) units to P persistent CTAs (rows = utterances x row_tiles):

@@ -25,7 +25,7 @@ yl = torch.full((B,), T_y, dtype=torch.int32, device=dev)
 for _ in range(3):
     pkg.fused_maximum_path(x_m, x_logs, z, xl, yl)
 torch.cuda.synchronize()
-buf = torch.zeros(2048, 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(2048, 32, dtype=torch.int64, device=dev)
 lib.mas_b200_debug_set_cycle_buffer(buf.data_ptr())
 pkg.fused_maximum_path(x_m, x_logs, z, xl, yl)
 torch.cuda.synchronize()
@@ -45,5 +45,9 @@ for c in range(K):
         col = col[col > 0]
         return (np.median(col - t0) / 1e3, (col.max() - t0) / 1e3) if len(col) else (float("nan"), float("nan"))
     teams = " ".join(f"{med(8 + t)[0]:6.1f}" for t in range(5) if (r[:, 8 + t] > 0).any())
-    print(f"  CTA {c}: start {med(0)[0]:5.1f} | operands {med(1)[0]:5.1f} | teams done {teams} | sweep done {med(4)[0]:6.1f} (max {med(4)[1]:6.1f})"
+    print(f"  CTA {c}: start {med(0)[0]:5.1f} | raw operands {med(26)[0]:5.1f}, element-wise {med(27)[0]:5.1f}, all {med(1)[0]:5.1f} | teams done {teams} | sweep done {med(4)[0]:6.1f} (max {med(4)[1]:6.1f})"
           f" | backtrack {med(5)[0]:6.1f} -> {med(6)[0]:6.1f} | output {med(7)[0]:6.1f} (max {med(7)[1]:6.1f})")
+    cyc = lambda k: float(np.median(r[:, k]))
+    nb = max(cyc(21), 1.0)
+    print(f"         sweep warp, cycles per 32-frame block ({nb:.0f} blocks): waits chunks {cyc(16) / nb:6.0f}, boundary {cyc(17) / nb:6.0f}, credit {cyc(18) / nb:6.0f};"
+          f" sweep {cyc(19) / nb:6.0f}, bits {cyc(22) / nb:5.0f}, boundary hand-back {cyc(23) / nb:5.0f}, consumed + zero fill {cyc(24) / nb:5.0f}; all {cyc(20) / nb:6.0f}")

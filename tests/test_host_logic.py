@@ -203,3 +203,32 @@ def test_sweep_plans(pkg):
         assert 2 <= S <= 4 and K in (1, 2, 4, 8) and W <= 15 and total <= max_smem
         if (B, T_x, T_y) in want:
             assert (R, W, K, bits_smem) == want[(B, T_x, T_y)], (B, T_x, T_y, out.tolist())
+
+
+def test_fused_geometry_for_the_benchmark_shapes(pkg):
+    """Kernel (2)'s launch geometry is pure host arithmetic (mas_fused.cu: make_geom / choose_geom):
+    cluster size, slice, FFMA teams and the shared-memory budget for the shapes bench.py times and for
+    random ones, on a B200's limits (148 SMs, 227 KB of opt-in shared memory per CTA)."""
+    lib = pkg._lib.load()
+    max_smem, num_sms = 232448 - 1024, 148
+    out = np.zeros(12, np.int32)
+    want = {  # (B, T_x, T_y) -> (CTAs per utterance, tokens per sweep lane, tokens per CTA, teams)
+        (32, 200, 1000): (4, 2, 50, 3),      # C2: 128 of 148 SMs, three contraction passes per slice
+        (256, 400, 2000): (8, 2, 50, 5),     # C3: 18 clusters of 8 at a time, bits still in shared memory
+        (8, 1024, 8192): (8, 4, 128, 3),     # C4: direction bits in the workspace
+    }
+    rng = np.random.default_rng(11)
+    cases = list(want) + [(int(rng.integers(1, 600)), int(rng.integers(1, 1025)), 0) for _ in range(300)]
+    for B, T_x, T_y in cases:
+        if T_y == 0:
+            T_y = int(rng.integers(max(T_x, 4), 8193)) // 4 * 4
+        rc = lib.mas_b200_debug_fused_geom(B, 80, T_x, T_y, max_smem, num_sms, out.ctypes.data)
+        assert rc == 0, (B, T_x, T_y, rc)
+        K, R, max_slice, nteams, team_warps, CG, F, NB, bits_smem, total, ffma_warps, ring_rows = (int(v) for v in out)
+        assert K in (1, 2, 4, 8) and 1 <= R <= 8 and max_slice % R == 0
+        assert max_slice * K >= T_x and max_slice <= 32 * R and ring_rows >= max_slice and ring_rows % 8 == 0
+        assert nteams * team_warps == ffma_warps and ffma_warps in (12, 15)
+        assert F == 8 * CG and -(-max_slice // 4) * CG <= 32 * team_warps      # a team's register tiles fit its threads
+        assert NB * 32 >= F + 64 and total <= max_smem
+        if (B, T_x, T_y) in want:
+            assert (K, R, max_slice, nteams) == want[(B, T_x, T_y)], (B, T_x, T_y, out.tolist())
