@@ -19,9 +19,10 @@
 //   * ONE sweep warp (warp 0) runs kernel (1)'s recurrence (mas_dp_cta.cuh: sweep_block) over the
 //     ring, 32 frames per step: waits for the teams' chunk counters (shared memory, acquire), takes the
 //     score of the slice's predecessor token from the previous CTA's sweep through distributed shared
-//     memory and hands its own last token's to the next CTA (st.async into the neighbour's 16-block
-//     boundary ring, completing bytes on the neighbour's mbarrier: data and signal in one message, no
-//     fence in the loop; credits come back as a plain remote store), packs the direction bits, frees
+//     memory and hands its own last token's to the next CTA (one 128-byte bulk copy per block into the
+//     neighbour's 16-block boundary ring, completing its bytes on the neighbour's mbarrier: data and
+//     signal in one message, no fence in the loop; credits come back as a plain remote store), packs
+//     the direction bits, frees
 //     the box (`consumed`, the producers' back-pressure), and drips bulk copies of a zero page into
 //     the dense output on the way.
 //   * backtrack by tokens, CTA K-1 -> 0 over DSMEM; ones, durations, frame -> token by all threads.
@@ -380,13 +381,13 @@ struct ZeroFill {
 // Returns non-zero when a real token of the slice ended with a non-finite score.
 //
 // Boundary protocol between the sweeps of neighbouring CTAs (token x0-1 of the previous CTA feeds
-// token x0 of this one): the previous CTA's publisher lane sends the four scores of every 16-byte
-// group with st.async into THIS CTA's boundary ring (kBndBlocks slots of 32 frames), each store
-// completing its bytes on the slot's mbarrier here; this warp arms a slot with arrive.expect_tx(128),
-// waits for its phase, sweeps, re-arms it and returns a credit (a plain remote store of the number
-// of consumed blocks -- it only guards the slot's reuse).  The previous CTA publishes blocks
-// [max(its first block, my first block - 1), its last block]; beyond its last block the boundary
-// token has left the band and whatever finite values the slot holds are never used.
+// token x0 of this one): the previous CTA's publisher lane parks the 32 scores of a block in a local
+// slot and sends them with ONE bulk copy into THIS CTA's boundary ring (kBndBlocks slots of 32
+// frames), completing 128 bytes on the slot's mbarrier here; this warp arms a slot with
+// arrive.expect_tx(128), waits for its phase, sweeps, re-arms it and returns a credit (a plain
+// remote store of the number of consumed blocks -- it only guards the slot's reuse).  The previous
+// CTA publishes blocks [max(its first block, my first block - 1), its last block]; beyond its last
+// block the boundary token has left the band and whatever finite values the slot holds are never used.
 template <int R, bool kDbg>
 __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned char *smem, int *ctl, float neg, ZeroFill &zf,
                                            uint32_t *bits_g, long long *dbg) {
@@ -396,7 +397,7 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
     // the dense output's zeros: all bulk copies now, while the sweep has nothing to do yet (the first
     // chunk of scores is a whole contraction pass away); they drain in the background
     if (lane == 0) zf.drip(zero_page, 0x7fffffff);
-    long long t_chunks = 0, t_prev = 0, t_credit = 0, t_core = 0, t_bits = 0, t_done = 0, t_fill = 0, t_begin = 0;
+    long long t_chunks = 0, t_prev = 0, t_credit = 0, t_core = 0, t_bits = 0, t_done = 0, t_fill = 0, t_begin = 0, t_core_tail = 0, t_all_tail = 0;
     if (kDbg) t_begin = clock64();
     if (u.cbend >= u.cb0) {
         float v[R];
@@ -405,6 +406,7 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
         for (int i = 0; i < R; ++i) v[i] = neg;
         float carry = (u.x0 == 0) ? 0.f : neg;              // frame 0 of token 0 starts from 0 (core.pyx:24-25)
         const uint32_t bnd_a = ptx::smem_u32(smem + g.off_bnd);
+        const uint32_t stage_a = bnd_a + kBndBlocks * kBlk * 4;           // outgoing boundary scores, one slot per block of the ring
         const uint32_t bnd_bar_a = ptx::smem_u32(smem + g.off_bar) + (uint32_t)(g.nteams * 2 * kStages) * 8u;   // [kBndBlocks]
         // ---- as the producer of the next CTA's boundary ----
         const bool has_next = u.x0 + u.n_c < u.tx;          // the next CTA has real tokens
@@ -510,8 +512,16 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
                 }
                 __syncwarp();
             }
-            systolic::sweep_block_ahead<R, 2, (R <= 3 ? 3 : 2)>(tile_a, lane_c, v, acc, carry, bnd_a + ring_slot, bnd_out_base + ring_slot,
-                                                               publishes && pub_lane, bar_out_base + (uint32_t)(cb & (kBndBlocks - 1)) * 8u);
+            // the publisher lane parks its last token's 32 scores in a local slot (predicated stores, nothing
+            // that splits the unrolled block) and sends them to the next CTA as ONE bulk copy that
+            // completes its bytes on the neighbour's mbarrier
+            systolic::sweep_block_ahead<R, 0, (R <= 3 ? 3 : 2)>(tile_a, lane_c, v, acc, carry, bnd_a + ring_slot, stage_a + ring_slot,
+                                                               publishes && pub_lane, 0u);
+            if (publishes && pub_lane) {
+                ptx::fence_proxy_async();
+                ptx::bulk_copy_s2peer(bnd_out_base + ring_slot, stage_a + ring_slot, kBlk * 4,
+                                      bar_out_base + (uint32_t)(cb & (kBndBlocks - 1)) * 8u);
+            }
             const long long t4 = kDbg ? clock64() : 0;
 #pragma unroll
             for (int i = 0; i < R; ++i) acc[i] = __brev(acc[i]);
@@ -541,6 +551,10 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
                 t_bits += t5 - t4;
                 t_done += t6 - t5;
                 t_fill += clock64() - t6;
+                if (cb > u.cbend - 8) {                     // the last eight blocks: the SM's FFMA warps are done by then
+                    t_core_tail += t4 - t3;
+                    t_all_tail += clock64() - t0;
+                }
             }
         }
         // a NaN or an infinity anywhere in a token's history is still in its score now
@@ -553,6 +567,7 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
         dbg[16] = t_chunks, dbg[17] = t_prev, dbg[18] = t_credit, dbg[19] = t_core;
         dbg[20] = clock64() - t_begin, dbg[21] = u.cbend - u.cb0 + 1;
         dbg[22] = t_bits, dbg[23] = t_done, dbg[24] = t_fill;
+        dbg[28] = t_core_tail, dbg[29] = t_all_tail;
     }
     if (lane == 0) {
         if (zf.total > 0) {
@@ -961,7 +976,7 @@ static int slice_frames(int T_x, int T_y, int max_slice) { return (T_y > T_x ? T
 static bool layout_geom(int D, int T_x, int max_smem, Geom &g) {
     int off = 0;
     g.off_zero = off, off += kZeroPage;
-    g.off_bnd = off, off += kBndBlocks * kBlk * 4;
+    g.off_bnd = off, off += 2 * kBndBlocks * kBlk * 4;      // incoming ring + outgoing staging slots
     g.off_run = off, off += (g.ring_rows + 2) * 8;
     g.off_xend = off, off += 2 * g.nblk * 4;               // + the "block map built" flags
     off = (int)align_up((size_t)off, 16);

@@ -144,6 +144,12 @@ __device__ __forceinline__ void bulk_store_s2g(void *gmem_dst, const void *smem_
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
+// bulk copy from this CTA's shared memory into a peer CTA's (shared::cluster addresses for the
+// destination and its mbarrier), completing `bytes` on that mbarrier
+__device__ __forceinline__ void bulk_copy_s2peer(uint32_t peer_dst, uint32_t local_src, uint32_t bytes, uint32_t peer_mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(peer_dst), "r"(local_src), "r"(bytes), "r"(peer_mbar) : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // waits until every committed bulk group has completed (its global writes are performed)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

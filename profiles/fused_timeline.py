@@ -50,4 +50,4 @@ for c in range(K):
     cyc = lambda k: float(np.median(r[:, k]))
     nb = max(cyc(21), 1.0)
     print(f"         sweep warp, cycles per 32-frame block ({nb:.0f} blocks): waits chunks {cyc(16) / nb:6.0f}, boundary {cyc(17) / nb:6.0f}, credit {cyc(18) / nb:6.0f};"
-          f" sweep {cyc(19) / nb:6.0f}, bits {cyc(22) / nb:5.0f}, boundary hand-back {cyc(23) / nb:5.0f}, consumed + zero fill {cyc(24) / nb:5.0f}; all {cyc(20) / nb:6.0f}")
+          f" sweep {cyc(19) / nb:6.0f}, bits {cyc(22) / nb:5.0f}, boundary hand-back {cyc(23) / nb:5.0f}, consumed + zero fill {cyc(24) / nb:5.0f}; all {cyc(20) / nb:6.0f}; last eight blocks: sweep {cyc(28) / 8:6.0f}, all {cyc(29) / 8:6.0f}")

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests -m gpu -x -q > gpurun_out/r2j_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2j_pytest.log
-tail -25 gpurun_out/r2j_pytest.log
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 120 python profiles/time_fused.py 2>&1 | tail -2
+timeout 300 python -m pytest tests/test_fused_gpu.py -x -q > gpurun_out/r2k_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2k_pytest.log
+tail -4 gpurun_out/r2k_pytest.log
+timeout 100 python profiles/fused_timeline.py 2>&1 | tail -9
+timeout 100 python profiles/time_fused.py 2>&1 | tail -2
