@@ -14,6 +14,10 @@ Two things are built, both only ever used as checkers / reported CPU baselines:
    OpenMP Cython").  Built only when ``/root/reference`` exists (i.e. in the build container);
    on the GPU box the prebuilt files are used.
 
+3. ``oracle/_ref/pkg/glow_tts_train/`` -- the reference's Python package (the modules the model and
+   its training step need), staged unmodified for the model-level checks on the GPU box
+   (``stage_reference_package``; git-ignored like the rest of ``oracle/_ref``).
+
 The shipped ``core.c`` of the reference does not compile on Python 3.12 (it includes the removed
 ``longintrepr.h``), so ``core.pyx`` is re-cythonized with the installed Cython, passing
 ``legacy_implicit_noexcept=True`` to keep Cython-0.29 ``nogil`` call semantics.
@@ -90,9 +94,47 @@ def build_reference(force: bool = False) -> dict:
     return result
 
 
+REF_PKG_DIR = REF_DIR / "pkg"            # oracle/_ref/pkg/glow_tts_train: the reference's Python package, staged for the GPU box
+
+# The modules the model-level checks import (SURVEY.md 8c "model-level oracle", 8d C5); the CLI, dataset,
+# export and inference modules are not needed and stay where they are.
+_REF_MODULES = ("__init__.py", "attentions.py", "checkpoint.py", "config.py", "layers.py", "models.py", "optimize.py",
+                "train.py", "utils.py", "monotonic_align/__init__.py")
+
+
+def stage_reference_package(force: bool = False):
+    """the model-level checks run the reference's OWN FlowGenerator and
+    train_step with `monotonic_align` swapped, on the GPU box -- where /root/reference does not
+    exist.  So the build container stages the package, unmodified, under the git-ignored
+    oracle/_ref/pkg/ (it travels with the snapshot like the compiled kernel; nothing of it enters the
+    repository's history) and puts the reference's compiled OpenMP kernel next to its wrapper.
+    Returns the staged package directory, or None when neither it nor /root/reference exists."""
+    dst = REF_PKG_DIR / "glow_tts_train"
+    src = REFERENCE_ROOT / "glow_tts_train"
+    if src.exists() and (force or not all((dst / m).exists() for m in _REF_MODULES)):
+        for m in _REF_MODULES:
+            (dst / m).parent.mkdir(parents=True, exist_ok=True)
+            shutil.copyfile(src / m, dst / m)
+    if not (dst / "models.py").exists():
+        return None
+    so = ref_so("omp")
+    if so.exists():
+        target = dst / "monotonic_align" / so.name
+        if not target.exists() or target.stat().st_mtime < so.stat().st_mtime:
+            shutil.copyfile(so, target)
+    stub = REF_PKG_DIR / "dataclasses_json" / "__init__.py"     # config.py:8 only needs the mixin's name
+    if not stub.exists():
+        stub.parent.mkdir(parents=True, exist_ok=True)
+        stub.write_text("class DataClassJsonMixin:\n    pass\n")
+    return dst
+
+
 def build_all(force: bool = False) -> dict:
     info = {"c_oracle": build_c_oracle(force)}
     info.update(build_reference(force))
+    pkg = stage_reference_package(force)
+    if pkg is not None:
+        info["reference_package"] = pkg
     return info
 
 
