@@ -32,6 +32,10 @@ EXPORTED_SYMBOLS = (
     "mas_b200_maximum_path_f32",
     "mas_b200_logp_f32",
     "mas_b200_fused_maximum_path_f32",
+    "mas_b200_duration_loss_f32",
+    "mas_b200_duration_loss_backward_f32",
+    "mas_b200_clip_grad_workspace_bytes",
+    "mas_b200_clip_grad_value_f32",
     "mas_b200_maximum_path_host_i32",
     "mas_b200_shutdown",
     "mas_b200_expand_prior_f32",
@@ -73,6 +77,14 @@ def load() -> ctypes.CDLL:
     lib.mas_b200_debug_path_plan.argtypes = [_i32, _i32, _i32, _i32, _i32, _vp]
     lib.mas_b200_debug_deal.restype = _i32
     lib.mas_b200_debug_deal.argtypes = [_i32, _i32, _i32, _vp, _vp]
+    lib.mas_b200_duration_loss_f32.restype = _i32
+    lib.mas_b200_duration_loss_f32.argtypes = [_vp, _vp, _vp, _vp, _i32, _i32, _vp]
+    lib.mas_b200_duration_loss_backward_f32.restype = _i32
+    lib.mas_b200_duration_loss_backward_f32.argtypes = [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]
+    lib.mas_b200_clip_grad_workspace_bytes.restype = _sz
+    lib.mas_b200_clip_grad_workspace_bytes.argtypes = [_i32]
+    lib.mas_b200_clip_grad_value_f32.restype = _i32
+    lib.mas_b200_clip_grad_value_f32.argtypes = [_vp, _vp, _i32, ctypes.c_float, _vp, _sz, _vp, _vp]
     lib.mas_b200_debug_fused_geom.restype = _i32
     lib.mas_b200_debug_fused_geom.argtypes = [_i32, _i32, _i32, _i32, _i32, _i32, _vp]
     lib.mas_b200_debug_force_unfused.restype = None

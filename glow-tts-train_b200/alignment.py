@@ -12,6 +12,7 @@ Reference call sites replaced (rhasspy/glow-tts-train):
 from __future__ import annotations
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -160,6 +161,9 @@ class _ExpandPrior(torch.autograd.Function):
             raise TypeError("x must be a float32 [B, D, T_x] tensor")
         x = x.contiguous()
         B, D, T_x = x.shape
+        if (frame_token.dim() != 2 or frame_token.shape[0] != B or tuple(durations.shape) != (B, T_x)
+                or frame_token.device != x.device or durations.device != x.device):
+            raise ValueError("frame_token must be [B, T_y] and durations [B, T_x], both on x's device")
         T_y = frame_token.shape[1]
         z = torch.empty((B, D, T_y), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
@@ -171,6 +175,7 @@ class _ExpandPrior(torch.autograd.Function):
         return z
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dz):
         lib = _lib.load()
         (durations,) = ctx.saved_tensors
@@ -198,11 +203,16 @@ def log_durations(durations, x_lengths):
     durations: fp32 [B, 1, T_x]."""
     lib = _lib.load()
     _require_cuda(durations, "durations")
+    if durations.dtype != torch.int32 or durations.dim() != 2:
+        raise TypeError("durations must be an int32 [B, T_x] tensor (as the alignment kernels return it)")
     B, T_x = durations.shape
+    durations = durations.contiguous()                      # (bound to a name: alive until the launch is enqueued)
     x_len = x_lengths.to(device=durations.device, dtype=torch.int32).contiguous()
+    if x_len.shape != (B,):
+        raise ValueError("x_lengths must have shape [B]")
     out = torch.empty((B, 1, T_x), dtype=torch.float32, device=durations.device)
     with torch.cuda.device(durations.device):
-        rc = lib.mas_b200_log_durations_f32(durations.contiguous().data_ptr(), x_len.data_ptr(), out.data_ptr(), B, T_x,
+        rc = lib.mas_b200_log_durations_f32(durations.data_ptr(), x_len.data_ptr(), out.data_ptr(), B, T_x,
                                             _stream(durations.device))
     _lib.check(rc, "mas_b200_log_durations_f32")
     return out
@@ -227,6 +237,7 @@ class _AlignedMleLoss(torch.autograd.Function):
         return out[0]
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         lib = _lib.load()
         z, x_m, x_logs, frame_token, durations, out = ctx.saved_tensors

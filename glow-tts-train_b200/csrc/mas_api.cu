@@ -277,6 +277,35 @@ int mas_b200_mle_loss_backward_f32(const float *z, const float *x_m, const float
                                     static_cast<cudaStream_t>(stream));
 }
 
+int mas_b200_duration_loss_f32(const float *logw, const int32_t *durations, const int32_t *x_len, float *loss_and_scale, int B,
+                               int T_x, mas_stream_t stream) {
+    if (B <= 0 || T_x <= 0) return MAS_ERR_INVALID_ARGUMENT;
+    if ((int64_t)B * T_x > (1 << 30)) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (!logw || !durations || !x_len || !loss_and_scale) return MAS_ERR_INVALID_ARGUMENT;
+    return launch_duration_loss(logw, durations, x_len, loss_and_scale, B, T_x, static_cast<cudaStream_t>(stream));
+}
+
+int mas_b200_duration_loss_backward_f32(const float *logw, const int32_t *durations, const int32_t *x_len, const float *scale,
+                                        float *dlogw, int B, int T_x, mas_stream_t stream) {
+    if (B <= 0 || T_x <= 0) return MAS_ERR_INVALID_ARGUMENT;
+    if ((int64_t)B * T_x > (1 << 30)) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (!logw || !durations || !x_len || !scale || !dlogw) return MAS_ERR_INVALID_ARGUMENT;
+    return launch_duration_loss_backward(logw, durations, x_len, scale, dlogw, B, T_x, static_cast<cudaStream_t>(stream));
+}
+
+size_t mas_b200_clip_grad_workspace_bytes(int nchunks) { return nchunks > 0 ? align_up((size_t)nchunks * sizeof(double), 256) : 0; }
+
+int mas_b200_clip_grad_value_f32(float *const *chunk_ptr, const int32_t *chunk_count, int nchunks, float clip_value, void *workspace,
+                                 size_t workspace_bytes, float *total_norm, mas_stream_t stream) {
+    if (nchunks < 0 || !(clip_value >= 0.f)) return MAS_ERR_INVALID_ARGUMENT;
+    if (!total_norm) return MAS_ERR_INVALID_ARGUMENT;
+    if (nchunks == 0) return cudaMemsetAsync(total_norm, 0, sizeof(float), static_cast<cudaStream_t>(stream)) == cudaSuccess ? MAS_OK : MAS_ERR_CUDA;
+    if (!chunk_ptr || !chunk_count) return MAS_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < mas_b200_clip_grad_workspace_bytes(nchunks)) return MAS_ERR_WORKSPACE_TOO_SMALL;
+    return launch_clip_grad_value(chunk_ptr, chunk_count, nchunks, clip_value, static_cast<double *>(workspace), total_norm,
+                                  static_cast<cudaStream_t>(stream));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-buffer entry: staging buffers are cached per device and grown on demand.
 // ---------------------------------------------------------------------------------------------

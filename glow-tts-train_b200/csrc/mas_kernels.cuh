@@ -84,6 +84,14 @@ int launch_mle_loss_backward(const float *z, const float *x_m, const float *x_lo
                              const int32_t *durations, const float *scale, float *dz, float *dx_m, float *dx_logs, int B, int D,
                              int T_x, int T_y, cudaStream_t stream);
 
+// the step around the path (mas_train.cu)
+int launch_duration_loss(const float *logw, const int32_t *durations, const int32_t *x_len, float *out2, int B, int T_x,
+                         cudaStream_t stream);
+int launch_duration_loss_backward(const float *logw, const int32_t *durations, const int32_t *x_len, const float *scale, float *dlogw,
+                                  int B, int T_x, cudaStream_t stream);
+int launch_clip_grad_value(float *const *chunk_ptr, const int32_t *chunk_count, int nchunks, float clip, double *partial,
+                           float *total_norm, cudaStream_t stream);
+
 // developer profiling hook: when non-null, kernels stamp clock64() phase times into it
 extern std::atomic<long long *> g_dbg_cycles;
 

@@ -208,6 +208,34 @@ int mas_b200_mle_loss_backward_f32(const float *z, const float *x_m, const float
                                    int D, int T_x, int T_y, mas_stream_t stream);
 
 /*
+ * SURVEY.md 8f rank 2, second half: `duration_loss(logw, logw_, lengths)` (glow_tts_train/utils.py:26-28,
+ * called at train.py:125) from the integer durations: logw_ = log(1e-8 + durations) for x < x_len, else 0
+ * (models.py:393) is formed on the fly,
+ *   loss = sum_{b,x} (logw[b,x] - logw_[b,x])^2 / sum_b x_len[b].
+ * logw fp32 [B][T_x] (the duration predictor's output, already masked as models.py:354 leaves it).
+ * loss_and_scale: 2 floats on the device: the loss and 2 / sum x_len (what the backward scales by).
+ * backward: `scale` = DEVICE pointer to (upstream gradient) x (2 / sum x_len); dlogw = scale (logw - logw_).
+ */
+int mas_b200_duration_loss_f32(const float *logw, const int32_t *durations, const int32_t *x_len, float *loss_and_scale, int B,
+                               int T_x, mas_stream_t stream);
+int mas_b200_duration_loss_backward_f32(const float *logw, const int32_t *durations, const int32_t *x_len, const float *scale,
+                                        float *dlogw, int B, int T_x, mas_stream_t stream);
+
+/*
+ * `clip_grad_value_(parameters, clip_value)` (glow_tts_train/utils.py:118-132, called
+ * at train.py:141/145) without a host synchronisation: the reference reads every gradient's norm back
+ * with `.item()` (one sync per parameter tensor and step).  Here the caller passes a DEVICE table of
+ * gradient chunks -- chunk_ptr[c] = first float of the chunk, chunk_count[c] = its length (a chunk is a
+ * slice of one gradient tensor; any split works, 64 K floats per chunk keep every SM busy) -- and one
+ * launch clamps every value to [-clip_value, clip_value] in place (NaN stays NaN, like torch.clamp_) and
+ * leaves total_norm[0] = sqrt(sum of squares of the UNclamped gradients) on the device, as the
+ * reference's return value.  Deterministic.  workspace: mas_b200_clip_grad_workspace_bytes(nchunks).
+ */
+size_t mas_b200_clip_grad_workspace_bytes(int nchunks);
+int mas_b200_clip_grad_value_f32(float *const *chunk_ptr, const int32_t *chunk_count, int nchunks, float clip_value, void *workspace,
+                                 size_t workspace_bytes, float *total_norm, mas_stream_t stream);
+
+/*
  * Host-buffer convenience used for end-to-end timing and by non-torch callers: takes HOST
  * pointers with the layout of maximum_path_c (core.pyx:40) -- values fp32 [B][T_x][T_y]
  * C-contiguous (NOT clobbered), t_xs / t_ys int32 [B], paths int32 [B][T_x][T_y] (fully written)

@@ -69,7 +69,10 @@ def run(steps=6, warmup=2, batch=32, t_text=200, t_mel=1000, n_speakers=4, gin_c
                      rm.synthetic_batch(batch, t_text, t_mel, n_speakers=n_speakers, seed=1234 + 17 * rank + i, device="cpu"))
                for i in range(warmup + steps)]
     out = {}
-    for name, module in (("reference", theirs), ("ours", pkg.monotonic_align)):
+    # "ours_no_sync": additionally the reference's train_step replaced by this package's restatement without
+    # its host synchronisations (.item() per step, and per parameter tensor in clip_grad_value_: SURVEY 8f-3)
+    for name, module, step_fn in (("reference", theirs, train.train_step), ("ours", pkg.monotonic_align, train.train_step),
+                                  ("ours_no_sync", pkg.monotonic_align, pkg.train_step)):
         config, model, optimizer = rm.make_model(ref, mean_only=mean_only, n_speakers=n_speakers, gin_channels=gin_channels,
                                                  device=dev, seed=1234)
         if world > 1:
@@ -77,13 +80,13 @@ def run(steps=6, warmup=2, batch=32, t_text=200, t_mel=1000, n_speakers=4, gin_c
         timed = TimedModule(module)
         prev = rm.swap_monotonic_align(ref, timed)
         try:
-            train.train_step(0, 0, model, optimizer, config, batches[:warmup], fp16_run=False)
+            step_fn(0, 0, model, optimizer, config, batches[:warmup], fp16_run=False)
             timed.events.clear()
             if dist is not None:
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            train.train_step(warmup, 0, model, optimizer, config, batches[warmup:], fp16_run=False)
+            step_fn(warmup, 0, model, optimizer, config, batches[warmup:], fp16_run=False)
             torch.cuda.synchronize()
             if dist is not None:
                 dist.barrier()
@@ -99,6 +102,7 @@ def run(steps=6, warmup=2, batch=32, t_text=200, t_mel=1000, n_speakers=4, gin_c
         torch.cuda.empty_cache()
     cells = batch * (t_text) * (t_mel // 2 * 2)
     out["speedup_step"] = out["reference"]["step_ms"] / out["ours"]["step_ms"]
+    out["speedup_step_no_sync"] = out["reference"]["step_ms"] / out["ours_no_sync"]["step_ms"]
     out["config"] = {"what": "reference train_step (train.py:91-162), fp32, multi-speaker Glow-TTS base", "n_gpus": world,
                      "per_gpu_batch": batch, "T_text": t_text, "T_mel": t_mel, "n_speakers": n_speakers, "gin_channels": gin_channels,
                      "mean_only": mean_only, "steps": steps, "ddp": world > 1, "lengths": "ragged", "cells_per_rank_step": cells}
