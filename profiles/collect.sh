@@ -9,7 +9,7 @@ set -u
 R=${1:-r1}
 WHAT=${2:-list}
 mkdir -p gpurun_out
-BENCH="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
+BENCH="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs --no-c5"
 FULL="ncu --set full --clock-control none --import-source on -c 1 -f"
 case "$WHAT" in
   list)

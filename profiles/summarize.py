@@ -20,7 +20,7 @@ for r in rows[1:]:
     per[r[ki]].append(float(r[vi].replace(",", "")))
 total = sum(sum(v) for v in per.values())
 with open(out / f"{R}_launches.txt", "w") as f:
-    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 5 --warmup 3 --no-cpu-baseline`\n")
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs --no-c5`\n")
     f.write("# per-launch times are cold-cache and serialised: compare SHARES\n")
     for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"{k[:90]:92s} n={len(v):4d} mean={sum(v) / len(v) / 1e3:9.1f} us share={sum(v) / total:6.1%}\n")
@@ -86,7 +86,11 @@ for tag in ("mas", "fused", "logp"):
                 f.write(f"#   {name:13s} instr {a:5d}..{b - 1:5d}: {n / max(tot, 1):6.1%} of samples ({top})\n")
             mix = collections.Counter((x[ia].split()[1] if x[ia].strip().startswith("@") else x[ia].split()[0]) for x in body[lo:hi + 1])
             f.write("#   hottest loop instruction mix: " + ", ".join(f"{k} {v}" for k, v in mix.most_common(8)) + "\n")
-json.dump({"c2": traffic.get("fused"), "c1": traffic.get("mas"), "fused_c2": traffic.get("fused"), "logp_c2": traffic.get("logp"),
-           "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, B=32 200x1000"},
-          open(out / "traffic.json", "w"), indent=1)
+# (a round that did not re-capture a kernel keeps the previous round's figure for it)
+prev = json.load(open(out / "traffic.json")) if (out / "traffic.json").exists() else {}
+new = {"c2": traffic.get("fused"), "c1": traffic.get("mas"), "fused_c2": traffic.get("fused"), "logp_c2": traffic.get("logp")}
+merged = {k: (v if v is not None else prev.get(k)) for k, v in new.items()}
+merged["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, B=32 200x1000"
+merged["captured_in"] = {**prev.get("captured_in", {}), **{k: R for k, v in new.items() if v is not None}}
+json.dump(merged, open(out / "traffic.json", "w"), indent=1)
 print(open(out / f"{R}_launches.txt").read())
