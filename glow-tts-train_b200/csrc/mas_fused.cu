@@ -617,11 +617,35 @@ __device__ __forceinline__ int walk_block(const uint32_t *row, int xl, int y, in
     return xl;
 }
 
+// The same walk by a whole warp (every lane passes the same arguments and gets the same result): the
+// direction words of the 32 tokens below the start come in with ONE load, lane i holding token
+// xl - i, and the chain runs on shuffles -- ~30 cycles per step instead of a dependent shared-memory
+// round trip for a lone thread (~120).  For the walks ON the backtrack's critical path.
+template <bool kSmem, bool kRecord>
+__device__ __forceinline__ int walk_block_warp(const uint32_t *row, int xl, int y, int x0, int col0, int *ylo, int lane) {
+    int base = xl, i = 0;
+    uint32_t mine = (base - lane >= 0) ? (kSmem ? row[base - lane] : __ldcg(row + base - lane)) : 0u;
+    while (xl >= 0 && x0 + xl > 0) {                        // token 0 is never left (core.pyx:34 `index != 0`)
+        if (i == 32) {
+            base = xl, i = 0;
+            mine = (base - lane >= 0) ? (kSmem ? row[base - lane] : __ldcg(row + base - lane)) : 0u;
+        }
+        const uint32_t w = __shfl_sync(0xffffffffu, mine, i) & (0xffffffffu >> (31 - y));
+        if (w == 0u) break;                                 // on this token since before the block
+        const int lo = 31 - __clz(w);                       // stepped onto it here
+        if (kRecord && lane == 0) ylo[xl] = col0 + lo;
+        --xl, ++i;
+        if (lo == 0) break;                                 // ... from the previous block's last frame
+        y = lo - 1;
+    }
+    return xl;
+}
+
 // Block maps of this CTA's slice for blocks cbl = first, first + step, ... as the sweep finishes them.
 template <bool kSmem>
-__device__ __forceinline__ void build_block_maps(const Geom &g, const Utt &u, const uint32_t *bits, unsigned char *maps, int *mapok,
-                                                 const int *ctl, int first, int step, int lane) {
-    const int nbox = u.cbend - u.cb0 + 1;
+__device__ __forceinline__ void build_block_maps(const Geom &g, const Utt &u, const uint32_t *bits, unsigned char *maps, const int *ctl,
+                                                 int first, int step, int lane) {
+    const int nbox = u.cbend - u.cb0;                       // (not the last block: a path only ever ENTERS a slice there)
     uint32_t spins = 0;
     for (int cbl = first; cbl < nbox; cbl += step) {
         while (ld_acquire_shared(ctl + kConsumed) <= cbl) {
@@ -633,8 +657,6 @@ __device__ __forceinline__ void build_block_maps(const Geom &g, const Utt &u, co
             const int r = walk_block<kSmem, false>(row, xl, 31, u.x0, 0, nullptr);
             maps[(size_t)cbl * g.ring_rows + xl] = (unsigned char)(r < 0 ? kLeft : xl - r);
         }
-        __syncwarp();
-        if (lane == 0) st_release_shared(mapok + cbl, 1);
     }
 }
 
@@ -703,7 +725,6 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
     int2 *run = reinterpret_cast<int2 *>(smem + g.off_run);       // redo path: [first frame, last frame] per token
     int *ylo = reinterpret_cast<int *>(smem + g.off_run);         // frame where the path steps onto each token (+ one past the top)
     int *xend = reinterpret_cast<int *>(smem + g.off_xend);       // token at the last frame of each block of the slice (-1: not composed)
-    int *mapok = xend + g.nblk;                                   // block map built?
     uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem + g.off_bits);
     unsigned char *maps_s = smem + g.off_maps;
     const float neg = pp.max_neg_val;
@@ -789,7 +810,7 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
             ptx::fence_barrier_init();
             ptx::mbar_arrive_expect_tx(bnd_bars + kBndBlocks, 8);
         }
-        for (int i = tid; i <= u.cbend - u.cb0; i += kThreads) xend[i] = -1, mapok[i] = 0;
+        for (int i = tid; i <= u.cbend - u.cb0; i += kThreads) xend[i] = -1;
         if (kDbg && dbg && tid == 0) dbg[0] = ptx::globaltimer_ns();
         ptx::cluster_sync();
 
@@ -819,9 +840,9 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
             // the warps on the other three schedulers, once their contraction is done: the backtrack's block maps
             const int bw = (warp - 1) - (warp >> 2);
             if (g.bits_in_smem)
-                build_block_maps<true>(g, u, bits_s, maps, mapok, ctl, bw, 12, lane);
+                build_block_maps<true>(g, u, bits_s, maps, ctl, bw, 12, lane);
             else
-                build_block_maps<false>(g, u, bits_w, maps, mapok, ctl, bw, 12, lane);
+                build_block_maps<false>(g, u, bits_w, maps, ctl, bw, 12, lane);
         }
         if (!g.bits_in_smem) __threadfence();
 
@@ -886,8 +907,9 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
             }
         } else {
             const uint32_t *bits_b = g.bits_in_smem ? bits_s : bits_w;
-            if (tid == 0 && c <= c_last) {
-                // compose the block maps from the entry point down; walk only the entry and the exit block
+            if (warp == 0 && c <= c_last) {
+                // (the whole sweep warp, uniformly) compose the block maps from the entry point down; walk only
+                // the entry block and the block where the path leaves the slice
                 int xl, y;
                 if (c == c_last) {
                     xl = u.tx - 1 - u.x0;
@@ -899,42 +921,52 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
                     xl = vctl[kBtToken] - u.x0;
                     y = vctl[kBtFrame];
                 }
-                ylo[xl + 1] = y + 1;                        // where the token above begins
+                const long long tb0 = kDbg ? clock64() : 0;
+                if (lane == 0) ylo[xl + 1] = y + 1;         // where the token above begins
                 int cb = y >> 5;
                 const uint32_t *row = bits_b + (size_t)cb * g.ring_rows;
-                xl = g.bits_in_smem ? walk_block<true, true>(row, xl, y & 31, u.x0, cb * kBlk, ylo)
-                                    : walk_block<false, true>(row, xl, y & 31, u.x0, cb * kBlk, ylo);
+                xl = g.bits_in_smem ? walk_block_warp<true, true>(row, xl, y & 31, u.x0, cb * kBlk, ylo, lane)
+                                    : walk_block_warp<false, true>(row, xl, y & 31, u.x0, cb * kBlk, ylo, lane);
+                const long long tb1 = kDbg ? clock64() : 0;
+                int nsteps = 0;
                 while (xl >= 0 && --cb >= u.cb0) {
-                    const int m = ld_acquire_shared(mapok + (cb - u.cb0)) ? maps[(size_t)(cb - u.cb0) * g.ring_rows + xl] : kLeft;
-                    if (m == kLeft) {                       // the path leaves the slice here (or nobody built this block's map)
+                    ++nsteps;
+                    // (every map below a slice's last block is complete: its builders passed the CTA barrier above;
+                    // the last block is only ever an entry block, walked directly, and nobody builds its map)
+                    const int m = maps[(size_t)(cb - u.cb0) * g.ring_rows + xl];
+                    if (m == kLeft) {                       // the path leaves the slice here
                         row = bits_b + (size_t)cb * g.ring_rows;
-                        xl = g.bits_in_smem ? walk_block<true, true>(row, xl, 31, u.x0, cb * kBlk, ylo)
-                                            : walk_block<false, true>(row, xl, 31, u.x0, cb * kBlk, ylo);
+                        xl = g.bits_in_smem ? walk_block_warp<true, true>(row, xl, 31, u.x0, cb * kBlk, ylo, lane)
+                                            : walk_block_warp<false, true>(row, xl, 31, u.x0, cb * kBlk, ylo, lane);
                         continue;
                     }
-                    xend[cb - u.cb0] = xl;
+                    if (lane == 0) xend[cb - u.cb0] = xl;
                     xl -= m;
                 }
-                if (c == 0) {
-                    ylo[0] = 0;
-                } else {
-                    ptx::st_async_b64(ptx::mapa(ptx::smem_u32(ctl + kBtToken), (uint32_t)(c - 1)),
-                                      (uint64_t)(uint32_t)(u.x0 - 1) | ((uint64_t)(uint32_t)(ylo[0] - 1) << 32),
-                                      ptx::mapa(bt_bar_a, (uint32_t)(c - 1)));
+                __syncwarp();
+                if (kDbg && dbg && lane == 0) dbg[30] = tb1 - tb0, dbg[31] = clock64() - tb1, dbg[25] = nsteps;
+                if (lane == 0) {
+                    if (c == 0) {
+                        ylo[0] = 0;
+                    } else {
+                        ptx::st_async_b64(ptx::mapa(ptx::smem_u32(ctl + kBtToken), (uint32_t)(c - 1)),
+                                          (uint64_t)(uint32_t)(u.x0 - 1) | ((uint64_t)(uint32_t)(ylo[0] - 1) << 32),
+                                          ptx::mapa(bt_bar_a, (uint32_t)(c - 1)));
+                    }
                 }
             }
             __syncthreads();
             if (kDbg && dbg && tid == 0) dbg[6] = ptx::globaltimer_ns();
-            // one lane per composed block: the frames where the path steps onto the tokens it visits there
-            if (warp < 4 && c <= c_last) {
-                for (int cbl = tid; cbl <= u.cbend - u.cb0; cbl += 128) {
+            // one warp per composed block: the frames where the path steps onto the tokens it visits there
+            if (c <= c_last) {
+                for (int cbl = warp; cbl <= u.cbend - u.cb0; cbl += kThreads / 32) {
                     const int xe = xend[cbl];
                     if (xe < 0) continue;
                     const uint32_t *row = bits_b + (size_t)(u.cb0 + cbl) * g.ring_rows;
                     if (g.bits_in_smem)
-                        walk_block<true, true>(row, xe, 31, u.x0, (u.cb0 + cbl) * kBlk, ylo);
+                        walk_block_warp<true, true>(row, xe, 31, u.x0, (u.cb0 + cbl) * kBlk, ylo, lane);
                     else
-                        walk_block<false, true>(row, xe, 31, u.x0, (u.cb0 + cbl) * kBlk, ylo);
+                        walk_block_warp<false, true>(row, xe, 31, u.x0, (u.cb0 + cbl) * kBlk, ylo, lane);
                 }
             }
             __syncthreads();
@@ -978,7 +1010,7 @@ static bool layout_geom(int D, int T_x, int max_smem, Geom &g) {
     g.off_zero = off, off += kZeroPage;
     g.off_bnd = off, off += 2 * kBndBlocks * kBlk * 4;      // incoming ring + outgoing staging slots
     g.off_run = off, off += (g.ring_rows + 2) * 8;
-    g.off_xend = off, off += 2 * g.nblk * 4;               // + the "block map built" flags
+    g.off_xend = off, off += g.nblk * 4;
     off = (int)align_up((size_t)off, 16);
     g.off_ctl = off, off += kCtlInts * 4;
     g.off_bar = off, off += (g.nteams * 2 * kStages + kBndBlocks + 1) * 8;

@@ -1,6 +1,6 @@
 """Timeline of the single-launch kernel (2) from globaltimer stamps (profiling hook): per CTA of a
 cluster -- operands staged, each FFMA team done, sweep done, backtrack done, output done.
-    python profiles/fused_timeline.py [B T_x T_y] [--mean-only]"""
+    python profiles/fused_timeline.py [B T_x T_y] [--mean-only] [--random]"""
 import sys
 from pathlib import Path
 
@@ -19,7 +19,12 @@ dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(1)
 x_m = torch.randn(B, D, T_x, generator=g).to(dev)
 x_logs = None if "--mean-only" in sys.argv else (0.3 * torch.randn(B, D, T_x, generator=g) - 0.5).to(dev)
-z = torch.randn(B, D, T_y, generator=g).to(dev)
+if "--random" in sys.argv:        # unstructured scores: long walks in the block maps and the backtrack
+    z = torch.randn(B, D, T_y, generator=g).to(dev)
+else:                             # "trained-like" (what bench.py times): z follows the token it belongs to
+    idx = (torch.arange(T_y) * T_x) // T_y
+    xl_cpu = torch.zeros(B, D, T_x) if x_logs is None else x_logs.cpu()
+    z = (x_m.cpu()[:, :, idx] + torch.exp(xl_cpu[:, :, idx]) * torch.randn(B, D, T_y, generator=g)).to(dev)
 xl = torch.full((B,), T_x, dtype=torch.int32, device=dev)
 yl = torch.full((B,), T_y, dtype=torch.int32, device=dev)
 for _ in range(3):
@@ -51,3 +56,4 @@ for c in range(K):
     nb = max(cyc(21), 1.0)
     print(f"         sweep warp, cycles per 32-frame block ({nb:.0f} blocks): waits chunks {cyc(16) / nb:6.0f}, boundary {cyc(17) / nb:6.0f}, credit {cyc(18) / nb:6.0f};"
           f" sweep {cyc(19) / nb:6.0f}, bits {cyc(22) / nb:5.0f}, boundary hand-back {cyc(23) / nb:5.0f}, consumed + zero fill {cyc(24) / nb:5.0f}; all {cyc(20) / nb:6.0f}; last eight blocks: sweep {cyc(28) / 8:6.0f}, all {cyc(29) / 8:6.0f}")
+    print(f"         backtrack thread: entry block walk {cyc(30):6.0f} cycles, {cyc(25):.0f} blocks composed (+ the exit block walked) {cyc(31):6.0f} cycles")
