@@ -70,6 +70,7 @@ enum Ctl { kTeamDone = 0, kConsumed = 8, kCredit = 11, kBtToken = 12, kBtFrame =
 
 struct Geom {
     int K, NC;                         // CTAs per cluster, clusters in the grid
+    int R;                             // tokens per sweep lane (the kernel's template parameter)
     int ffma_all;                      // 15 FFMA warps (all but the sweep warp) or 12 (the sweep warp's scheduler stays free)
     int nteams, team_warps;
     int max_slice, tr_max, ring_rows;  // tokens per CTA (bound), the same rounded up to 4 / to 8
@@ -99,6 +100,13 @@ struct Utt {
     int f_lo, f_hi;                    // frames [f_lo, f_hi) are contracted: the band of the slice, to multiples of 8
     int nch;                           // chunks to contract
 };
+
+// Swizzle of a score-ring box: the 16-byte group g of row q sits at group (g ^ key(q)).  kernel (1)'s TMA
+// boxes use the hardware's key (q & 7); the sweep lane l reads rows l R .. l R + R - 1, so with an even R
+// the eight lanes of a quarter warp share keys and every LDS.128 of the block is a 2- (R = 2) to 8-way
+// (R = 8) bank conflict.  This ring is written by the FFMA warps, not by TMA, so the key is free:
+// the LANE that owns the row -- eight consecutive lanes, eight different keys, for every R.
+__device__ __forceinline__ uint32_t row_key(int q, int R) { return (uint32_t)((q / R) & 7); }
 
 __device__ __forceinline__ void named_sync(int bar, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthr) : "memory"); }
 __device__ __forceinline__ int ld_acquire_shared(const int *p) { return ptx::ld_acquire_shared_a(ptx::smem_u32(p)); }
@@ -218,7 +226,10 @@ __device__ __forceinline__ int team_contract(const CUtensorMap &tmap_z, const Ge
     const int D = p.D, F = u.F, CG = u.CG, TR = u.TR, NB = g.NB;
     const float *sInv = reinterpret_cast<const float *>(smem + g.off_ops), *sMiv = sInv + D * TR;
     const float *sL1 = reinterpret_cast<const float *>(smem + g.off_l14), *sL4 = sL1 + g.tr_max;
-    float *sL2 = reinterpret_cast<float *>(smem + g.off_l2) + team * g.F_cap;
+    // per-frame sums of the mean_only mode, two copies used alternately: with few channels a fast warp is
+    // through the next chunk's panels (all of them already landed) before a slow one has finished the
+    // stores that read this chunk's sums; the per-chunk barrier keeps them less than two chunks apart
+    float *sL2_base = reinterpret_cast<float *>(smem + g.off_l2) + team * 2 * g.F_cap;
     const uint32_t ring_a = ptx::smem_u32(smem + g.off_ring), box_bytes = (uint32_t)g.ring_rows * 128u;
     ZPipe zp;
     zp.stage_floats = kChan * g.F_cap;
@@ -293,6 +304,7 @@ __device__ __forceinline__ int team_contract(const CUtensorMap &tmap_z, const Ge
                 if (++spins > kSpinLimit) systolic::spin_fail();
             }
         }
+        float *sL2 = sL2_base + (count & 1) * g.F_cap;
         if (kMeanOnly && ttid < F) sL2[ttid] = l2;
         if (count == 0) named_sync(kBarFfma, g.nteams * tn);   // the row constants are summed (stage_ops)
         named_sync(bar, tn);                                // the ring has room (and the frame sums are there)
@@ -323,7 +335,7 @@ __device__ __forceinline__ int team_contract(const CUtensorMap &tmap_z, const Ge
                         r.w = logp_cell_finish(l1, cq[3], l4);
                     }
                     const int bx = (f >> 5) - u.cb0, slot = bx % NB, gq = (f & 31) >> 2;
-                    ptx::st_shared_v4_if(true, row_a + (uint32_t)slot * box_bytes + (uint32_t)((gq ^ (xr & 7)) << 4), r);
+                    ptx::st_shared_v4_if(true, row_a + (uint32_t)slot * box_bytes + (((uint32_t)gq ^ row_key(xr, g.R)) << 4), r);
                 }
             }
         }
@@ -352,7 +364,7 @@ __device__ __forceinline__ void zero_below_diagonal_rows(uint32_t tile_a, int la
 #pragma unroll
         for (int cidx = 0; cidx < 8; ++cidx) {
             if (4 * cidx >= d) break;
-            const uint32_t a = row_a + (uint32_t)((cidx ^ (q & 7)) << 4);
+            const uint32_t a = row_a + (((uint32_t)cidx ^ row_key(q, R)) << 4);
             float4 x = ptx::ld_shared_v4(a);
             x.x = 0.f;
             if (4 * cidx + 1 < d) x.y = 0.f;
@@ -428,7 +440,7 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             const int row = min(lane * R + i, u.TR - 1);   // lanes beyond the tile re-read its last row (their tokens are inert)
-            lane_c[i] = (uint32_t)(row * 128) | (uint32_t)((row & 7) << 4);
+            lane_c[i] = (uint32_t)(row * 128) | (row_key(row, R) << 4);
         }
         const uint32_t ring_a = ptx::smem_u32(smem + g.off_ring), box_bytes = (uint32_t)g.ring_rows * 128u;
         uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem + g.off_bits);
@@ -508,7 +520,7 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
                     const int q = lane * R + i;
                     if (q >= u.TR) continue;
                     for (int cidx = (u.f_hi - col0) >> 2; cidx < 8; ++cidx)
-                        ptx::st_shared_v4_if(true, tile_a + (uint32_t)q * 128u + (uint32_t)((cidx ^ (q & 7)) << 4), make_float4(0.f, 0.f, 0.f, 0.f));
+                        ptx::st_shared_v4_if(true, tile_a + (uint32_t)q * 128u + (((uint32_t)cidx ^ row_key(q, R)) << 4), make_float4(0.f, 0.f, 0.f, 0.f));
                 }
                 __syncwarp();
             }
@@ -1021,7 +1033,7 @@ static bool layout_geom(int D, int T_x, int max_smem, Geom &g) {
     g.off_part = off, off += 8 * g.tr_max * 4;
     off = (int)align_up((size_t)off, 128);
     g.off_z = off, off += g.nteams * kStages * kChan * g.F_cap * 4;   // TMA destinations: 128-byte aligned (F_cap is even)
-    g.off_l2 = off, off += g.nteams * g.F_cap * 4;
+    g.off_l2 = off, off += g.nteams * 2 * g.F_cap * 4;
     off = (int)align_up((size_t)off, 1024);
     g.off_ring = off;
     const int box = g.ring_rows * 128;
@@ -1060,6 +1072,7 @@ static bool make_geom(int D, int T_x, int T_y, int K, int ffma_all, int teams_fo
     const int R = tokens_per_lane(T_x, K);
     if (R > 8) return false;
     g0.K = K;
+    g0.R = R;
     g0.ffma_all = ffma_all;
     g0.max_slice = ceil_div(ceil_div(T_x, K), R) * R;
     g0.tr_max = ceil_div(g0.max_slice, kGemmTM) * kGemmTM;

