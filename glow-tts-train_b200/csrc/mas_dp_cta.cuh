@@ -337,6 +337,48 @@ __device__ __forceinline__ int backtrack_tokens(const uint32_t *bits, int rows, 
     return y_hi;
 }
 
+// The same backtrack by a whole WARP, for direction bits in the L2-resident WORKSPACE (long
+// utterances), where a lone thread pays an L2 round trip (~700 cycles) per step and the walk was 28 % of
+// a CTA's time (400 x 2000): the direction words of the 32 tokens below the current one come in with ONE
+// coalesced load per 32-frame block (lane i: token x - i) and the steps inside the block run on shuffles;
+// only moving to the block above costs a load again (404 -> 379 us at B=256, 400 x 2000).  Every lane
+// passes the same arguments and gets the same result; lane 0 writes the run table.  For bits in SHARED
+// memory the tuned single-thread walk above is faster (62 against ~100 cycles per step: measured,
+// profiles/r2_sweep_k.txt), so that case keeps it.
+template <bool kSmem>
+__device__ __forceinline__ int backtrack_tokens_warp(const uint32_t *bits, int rows, int xc, int x, int y_hi, int x_min, int2 *run,
+                                                     int lane) {
+    run -= xc;                                              // indexed by the global token number
+    int scan = y_hi;                                        // frame the search for the step onto x starts from
+    while (x >= x_min && scan >= 0) {
+        const int cb = scan >> 5, col0 = cb << 5;
+        const uint32_t *row = bits + (size_t)cb * rows - xc;
+        const int t = x - lane;
+        const uint32_t mine = (t >= x_min) ? (kSmem ? row[t] : __ldcg(row + t)) : 0u;
+        int y = scan & 31;
+        bool up = false;                                    // continue in the block above?
+#pragma unroll 1
+        for (int i = 0; i < 32 && x >= x_min; ++i) {
+            const uint32_t w = __shfl_sync(0xffffffffu, mine, i) & (0xffffffffu >> (31 - y));
+            if (w == 0u) {                                  // on this token since before the block
+                up = true;
+                break;
+            }
+            const int lo = 31 - __clz(w);                   // stepped onto x at frame col0 + lo
+            if (lane == 0) run[x] = make_int2(col0 + lo, y_hi);
+            y_hi = col0 + lo - 1;
+            --x;
+            if (lo == 0) {                                  // the next token ends at the block above's last frame
+                up = true;
+                break;
+            }
+            y = lo - 1;
+        }
+        scan = up ? col0 - 1 : col0 + y;                    // (else: 32 tokens inside one block: reload from the new x)
+    }
+    return y_hi;
+}
+
 // The whole per-CTA program of kernel (1): lengths, sweep, (exact redo), backtrack, dense output.
 // kCluster: compiled with the distributed-shared-memory paths (K > 1); the K == 1 build carries none.
 // `b`: utterance; `cta_tag`: index for the profiling buffer; warps beyond plan.W + 1 idle.
@@ -700,7 +742,7 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
         dbg[12] = ptx::globaltimer_ns();
     }
     const int c_last = (tx > 0) ? (tx - 1) / rows : -1;          // CTA that owns the last token
-    if (tid == 0 && c <= c_last) {
+    if (warp == 0 && c <= c_last) {                              // (the whole first warp, uniformly)
         int x, y_hi;
         if (c == c_last) {
             x = tx - 1;
@@ -713,16 +755,23 @@ __device__ __forceinline__ void dp_cta(const CUtensorMap &tmap, const PathParams
             y_hi = misc[2];
         }
         const int x_min = max(xc, 1);
-        if (x >= x_min)
-            y_hi = bits_from_smem ? backtrack_tokens<true>(bits_s, rows, xc, x, y_hi, x_min, run)
-                                  : backtrack_tokens<false>(bits_g, rows, xc, x, y_hi, x_min, run);
-        if (!kCluster || c == 0) {
-            run[0] = make_int2(0, y_hi);
-        } else {
-            const uint32_t peer = ptx::mapa(ptx::smem_u32(const_cast<int *>(&misc[0])), (uint32_t)(c - 1));
-            ptx::st_cluster_u32(peer + 4, (uint32_t)(xc - 1));
-            ptx::st_cluster_u32(peer + 8, (uint32_t)y_hi);
-            ptx::st_release_cluster_if(true, peer, 1);
+        if (x >= x_min) {
+            if (!bits_from_smem)
+                y_hi = backtrack_tokens_warp<false>(bits_g, rows, xc, x, y_hi, x_min, run, lane);
+            else if (lane == 0)
+                y_hi = backtrack_tokens<true>(bits_s, rows, xc, x, y_hi, x_min, run);
+            y_hi = __shfl_sync(0xffffffffu, y_hi, 0);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (!kCluster || c == 0) {
+                run[0] = make_int2(0, y_hi);
+            } else {
+                const uint32_t peer = ptx::mapa(ptx::smem_u32(const_cast<int *>(&misc[0])), (uint32_t)(c - 1));
+                ptx::st_cluster_u32(peer + 4, (uint32_t)(xc - 1));
+                ptx::st_cluster_u32(peer + 8, (uint32_t)y_hi);
+                ptx::st_release_cluster_if(true, peer, 1);
+            }
         }
     }
     if (kDbg && dbg && tid == 0) dbg[6] = clock64();

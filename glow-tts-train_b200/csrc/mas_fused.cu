@@ -885,7 +885,7 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
         if (redo) {
             // (rare) the redo's direction words are in global memory, tokens strided by the slice: the
             // serial token walk of kernel (1)
-            if (tid == 0 && c <= c_last) {
+            if (warp == 0 && c <= c_last) {
                 int x, y_hi;
                 if (c == c_last) {
                     x = u.tx - 1;
@@ -898,13 +898,16 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
                     y_hi = vctl[kBtFrame];
                 }
                 const int x_min = max(u.x0, 1);
-                if (x >= x_min) y_hi = systolic::backtrack_tokens<false>(bits_gl, bits_rows, u.x0, x, y_hi, x_min, run);
-                if (c == 0) {
-                    run[0] = make_int2(0, y_hi);
-                } else {
-                    const uint32_t peer = ptx::mapa(ptx::smem_u32(ctl + kBtToken), (uint32_t)(c - 1));   // (8-byte aligned)
-                    ptx::st_async_b64(peer, (uint64_t)(uint32_t)(u.x0 - 1) | ((uint64_t)(uint32_t)y_hi << 32),
-                                      ptx::mapa(bt_bar_a, (uint32_t)(c - 1)));
+                if (x >= x_min) y_hi = systolic::backtrack_tokens_warp<false>(bits_gl, bits_rows, u.x0, x, y_hi, x_min, run, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    if (c == 0) {
+                        run[0] = make_int2(0, y_hi);
+                    } else {
+                        const uint32_t peer = ptx::mapa(ptx::smem_u32(ctl + kBtToken), (uint32_t)(c - 1));   // (8-byte aligned)
+                        ptx::st_async_b64(peer, (uint64_t)(uint32_t)(u.x0 - 1) | ((uint64_t)(uint32_t)y_hi << 32),
+                                          ptx::mapa(bt_bar_a, (uint32_t)(c - 1)));
+                    }
                 }
             }
             __syncthreads();
