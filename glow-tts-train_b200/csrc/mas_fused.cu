@@ -78,6 +78,7 @@ struct Geom {
     int NB;                            // score ring depth in 32-frame boxes
     int nblk, bits_in_smem;
     int ops_tmp3;                      // the ring has room for stage_ops' third scratch array (exp(-2 logs))
+    int use_maps;                      // build the backtrack's block maps while the sweep runs (short slices only)
     int passes;                        // contraction passes of a full-length utterance (host estimate)
     int nsh, dsh;                      // channel shares of the row constants, as the materialising kernel sums them
     int off_zero, off_bnd, off_run, off_xend, off_ctl, off_bar, off_big, off_ops, off_l14, off_part, off_z, off_l2, off_ring, off_bits,
@@ -848,7 +849,7 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
         }
         uint32_t *const bits_w = g.bits_in_smem ? nullptr : g.ws_bits + ((size_t)cluster_id * K + c) * g.nblk * g.ring_rows;
         unsigned char *const maps = g.bits_in_smem ? maps_s : g.ws_maps + ((size_t)cluster_id * K + c) * g.nblk * g.ring_rows;
-        if ((warp & 3) != 0 && active) {
+        if (g.use_maps && (warp & 3) != 0 && active) {
             // the warps on the other three schedulers, once their contraction is done: the backtrack's block maps
             const int bw = (warp - 1) - (warp >> 2);
             if (g.bits_in_smem)
@@ -882,9 +883,10 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
         const int c_last = (u.tx > 0) ? (u.tx - 1) / u.n_c : -1;   // CTA that owns the last token
         const uint32_t bt_bar_a = ptx::smem_u32(bnd_bars + kBndBlocks);
         float *out = pp.path + (int64_t)b * T_x * T_y;
-        if (redo) {
-            // (rare) the redo's direction words are in global memory, tokens strided by the slice: the
-            // serial token walk of kernel (1)
+        if (redo || !g.use_maps) {
+            // the token walk of kernel (1), CTA after CTA: for long slices (tabulating the block maps costs
+            // the builders more than the maps save: 39 us of maps for an 11 us backtrack at 400 x 2000), and
+            // after a redo (rare; its direction words are in global memory, tokens strided by the slice)
             if (warp == 0 && c <= c_last) {
                 int x, y_hi;
                 if (c == c_last) {
@@ -898,7 +900,14 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
                     y_hi = vctl[kBtFrame];
                 }
                 const int x_min = max(u.x0, 1);
-                if (x >= x_min) y_hi = systolic::backtrack_tokens_warp<false>(bits_gl, bits_rows, u.x0, x, y_hi, x_min, run, lane);
+                if (x >= x_min) {
+                    // (shared memory: the lone thread's tuned walk; workspace: one coalesced load per block, mas_dp_cta.cuh)
+                    if (bits_gl != nullptr)
+                        y_hi = systolic::backtrack_tokens_warp<false>(bits_gl, bits_rows, u.x0, x, y_hi, x_min, run, lane);
+                    else if (lane == 0)
+                        y_hi = systolic::backtrack_tokens<true>(bits_s, bits_rows, u.x0, x, y_hi, x_min, run);
+                    y_hi = __shfl_sync(0xffffffffu, y_hi, 0);
+                }
                 __syncwarp();
                 if (lane == 0) {
                     if (c == 0) {
@@ -1051,11 +1060,15 @@ static bool layout_geom(int D, int T_x, int max_smem, Geom &g) {
         const int left = max_smem - g.off_ring - (bits_smem ? bits_bytes : 0);
         int nb = left / box;
         if (nb > 32) nb = 32;
-        // the direction bits leave shared memory before the ring gets too shallow for the teams
-        if (nb >= (bits_smem ? ceil_div((g.nteams + 1) * g.F_cap + 2 * kBlk, kBlk) : nb_floor)) {
+        // the direction bits and block maps stay in shared memory as long as the ring still holds two
+        // chunks and the box being swept: in the workspace every step of the map builders and of the
+        // backtrack is an L2 round trip (400 x 2000: 170 us per utterance against 20)
+        const int nb_bits = ceil_div(2 * g.F_cap + 2 * kBlk, kBlk) > nb_floor ? ceil_div(2 * g.F_cap + 2 * kBlk, kBlk) : nb_floor;
+        if (nb >= (bits_smem ? nb_bits : nb_floor)) {
             g.NB = nb;
             g.bits_in_smem = bits_smem;
             g.ops_tmp3 = (int64_t)nb * box >= (int64_t)3 * D * g.tr_max * 4;
+            g.use_maps = bits_smem && g.max_slice <= 64;
             g.off_bits = g.off_ring + nb * box;
             g.off_maps = g.off_bits + g.nblk * g.ring_rows * 4;
             g.total = g.off_bits + (bits_smem ? bits_bytes : 0);
@@ -1163,7 +1176,9 @@ static double estimate_us(const Geom &g, int B, int num_sms) {
     const int nc = num_sms / g.K < 1 ? 1 : num_sms / g.K;
     const int rounds = ceil_div(B, nc);
     const int slice_blocks = ceil_div(g.passes * g.nteams * g.F_cap, kBlk);
-    return rounds * (g.passes * 18.4 + 25.0 + 4.0 * g.K + (g.bits_in_smem ? 0.0 : 3.0 * slice_blocks));
+    // (the serial token walk of long slices: ~0.05 us per token and CTA hop; from the workspace ~0.4 us per block more)
+    const double walk = g.use_maps ? 0.0 : 0.05 * g.max_slice * g.K + (g.bits_in_smem ? 0.0 : 0.4 * slice_blocks * g.K);
+    return rounds * (g.passes * 18.4 + 25.0 + 4.0 * g.K + walk);
 }
 // ... and the two kernels back to back: the materialising kernel's rounds of (token tile, chunk)
 // units (16.5 us each on every SM, mas_logp.cu) + kernel (1) (latency floor 41 ns per frame, else
@@ -1173,7 +1188,10 @@ static double estimate_two_kernels_us(int B, int T_x, int T_y) {
     const double units = (double)B * t.row_tiles * t.nchunks;
     const double logp_us = ceil(units / 148.0) * 16.5 + 6.0;
     const double cells = (double)B * T_x * T_y;
-    const double k1 = cells / 0.5e6 > 0.041 * T_y ? cells / 0.5e6 : 0.041 * T_y;
+    // kernel (1): ~500 Gcells/s once every SM streams, else the dependent chain: 41 ns per frame with up to
+    // three sweep warps (<= 288 tokens), 53 ns with more (measured: profiles/r2_sweep_k.txt)
+    const double per_frame = T_x <= 288 ? 0.041 : 0.0535;
+    const double k1 = cells / 0.5e6 > per_frame * T_y ? cells / 0.5e6 : per_frame * T_y;
     return logp_us + k1 + 5.0;
 }
 

@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-: > gpurun_out/r2_sweep_k.txt
-for shp in "32 200 1000" "148 200 1000" "592 200 1000" "256 400 2000" "32 400 2000" "8 1024 8192" "32 1024 8192"; do
-  timeout 120 python profiles/sweep_k.py $shp 0 2>&1 | tail -1 >> gpurun_out/r2_sweep_k.txt
+timeout 300 python -m pytest tests/test_fused_gpu.py -x -q 2>&1 | tail -2
+for shp in "32 400 2000" "64 400 2000" "32 200 1000" "128 400 2000"; do
+  echo "== $shp (by estimate)"; MAS_B200_DEBUG=1 timeout 120 python profiles/time_fused.py $shp 2>&1 | grep -m2 "estimates\|not taken" | cut -c1-150; timeout 120 python profiles/time_fused.py $shp 2>&1 | tail -2
 done
-cat gpurun_out/r2_sweep_k.txt

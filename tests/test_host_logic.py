@@ -214,7 +214,7 @@ def test_fused_geometry_for_the_benchmark_shapes(pkg):
     out = np.zeros(12, np.int32)
     want = {  # (B, T_x, T_y) -> (CTAs per utterance, tokens per sweep lane, tokens per CTA, teams)
         (32, 200, 1000): (4, 2, 50, 3),      # C2: 128 of 148 SMs, three contraction passes per slice
-        (256, 400, 2000): (8, 2, 50, 5),     # C3: 18 clusters of 8 at a time, bits still in shared memory
+        (256, 400, 2000): (4, 4, 100, 3),    # C3: 37 clusters at a time, direction bits in shared memory behind a 6-box ring
         (8, 1024, 8192): (8, 4, 128, 3),     # C4: direction bits in the workspace
     }
     rng = np.random.default_rng(11)
