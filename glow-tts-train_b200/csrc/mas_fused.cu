@@ -1068,7 +1068,8 @@ static bool layout_geom(int D, int T_x, int max_smem, Geom &g) {
             g.NB = nb;
             g.bits_in_smem = bits_smem;
             g.ops_tmp3 = (int64_t)nb * box >= (int64_t)3 * D * g.tr_max * 4;
-            g.use_maps = bits_smem && g.max_slice <= 64;
+            static const char *maps_env = getenv("MAS_B200_FUSED_MAPS");           // experiment hook
+            g.use_maps = maps_env ? atoi(maps_env) != 0 && bits_smem : (bits_smem && g.max_slice <= 64);
             g.off_bits = g.off_ring + nb * box;
             g.off_maps = g.off_bits + g.nblk * g.ring_rows * 4;
             g.total = g.off_bits + (bits_smem ? bits_bytes : 0);
