@@ -66,8 +66,9 @@ __host__ __device__ inline Plan make_plan(int R, int W, int S, int K, int T_y, b
 
 __device__ __forceinline__ void spin_fail() { __trap(); }
 
-// The threads that run one utterance's program: a whole CTA (hardware barrier 0), or -- in the
-// single launch, where two utterances share a sweep CTA -- one half of it with a barrier of its own.
+// The threads that run one utterance's program: a whole CTA (hardware barrier 0), or a part of one
+// with a named barrier of its own (round 1 measured two utterances per CTA that way: slower, not kept;
+// the exact-sweep helpers still take the abstraction).
 struct Team {
     int tid, nthr, bar;
     __device__ __forceinline__ void sync() const {
@@ -816,8 +817,8 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // Tokens per lane (R) and sweep warps (W) for `tokens` tokens in one CTA.  The sweep is a chain of
-// (blocks + W - 1) steps; what a step costs was measured per R on B200 (profiles/sweep_k.py with
-// MAS_B200_FORCE_R, 32-frame blocks, cycles): the in-order warp eats one shuffle latency per frame
+// (blocks + W - 1) steps; what a step costs was measured per R on B200 (32-frame blocks, cycles;
+// `python profiles/measure_step_costs.py` re-measures the table on the device at hand): the in-order warp eats one shuffle latency per frame
 // whatever R is, so two or three tokens per lane cost the same per step and three need fewer warps
 // (less skew); four is an outlier of nvcc's schedule and is only taken when nothing else fits.
 inline bool choose_shape(int tokens, int &R, int &W) {

@@ -144,11 +144,15 @@ int mas_b200_logp_f32(const float *x_m, const float *x_logs, const float *z, flo
                       int B, int D, int T_x, int T_y, mas_stream_t stream);
 
 /*
- * Kernel (2): log-likelihood + alignment search in one launch: producer CTAs contract the scores in
- * chunks of 64-128 frames, sweep CTAs consume them as they appear (ready flags), through an
- * L2-resident scratch in the workspace.  Batches too large for one wave (more than ~#SMs/3
- * utterances) and shapes the single launch does not support run as two launches inside the same
- * call, same results.  Replaces models.py:362-382 (+ :393 through `durations`).
+ * Kernel (2): log-likelihood + alignment search in one call (models.py:362-382, + :393 through
+ * `durations`).  The single launch gives every utterance a thread-block cluster of CTAs that slice its
+ * tokens; each CTA contracts its slice's scores over the channels into a ring in SHARED memory and
+ * sweeps them there (neighbouring CTAs exchange one boundary token's scores over distributed shared
+ * memory), so the [B,T_x,T_y] score matrix is never materialised and the workspace holds only the
+ * scratch of the rare literal redo (non-finite scores).  Any batch size runs in that one launch; where
+ * the entry's cost estimate says the two kernels back to back (scores of a group of utterances staged
+ * in the workspace, at most 256 MB) are faster -- several rounds of utterances per cluster, frame
+ * counts that are not a multiple of 4, > 80 channels -- it runs those instead: same results.
  *   x_len, y_len int32 [B] device: valid tokens / frames (what the prefix masks encode).
  * Other arguments as above.  logp tiles are accurate to 1e-5 relative against the fp64 formula;
  * the path equals kernel (1) run on mas_b200_logp_f32's output bit for bit.
