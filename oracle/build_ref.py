@@ -14,9 +14,9 @@ Two things are built, both only ever used as checkers / reported CPU baselines:
    OpenMP Cython").  Built only when ``/root/reference`` exists (i.e. in the build container);
    on the GPU box the prebuilt files are used.
 
-3. ``oracle/_ref/pkg/glow_tts_train/`` -- the reference's Python package (the modules the model and
-   its training step need), staged unmodified for the model-level checks on the GPU box
-   (``stage_reference_package``; git-ignored like the rest of ``oracle/_ref``).
+3. ``oracle/_ref/refpkg.zip`` -- the reference's Python package (the modules the model and its
+   training step need, unmodified) + its compiled OpenMP kernel, packed for the model-level checks on
+   the GPU box (``stage_reference_package``; git-ignored like the rest of ``oracle/_ref``).
 
 The shipped ``core.c`` of the reference does not compile on Python 3.12 (it includes the removed
 ``longintrepr.h``), so ``core.pyx`` is re-cythonized with the installed Cython, passing
@@ -94,7 +94,7 @@ def build_reference(force: bool = False) -> dict:
     return result
 
 
-REF_PKG_DIR = REF_DIR / "pkg"            # oracle/_ref/pkg/glow_tts_train: the reference's Python package, staged for the GPU box
+REF_PKG_ZIP = REF_DIR / "refpkg.zip"     # the reference's Python package, staged as ONE archive for the GPU box
 
 # The modules the model-level checks import (SURVEY.md 8c "model-level oracle", 8d C5); the CLI, dataset,
 # export and inference modules are not needed and stay where they are.
@@ -105,28 +105,28 @@ _REF_MODULES = ("__init__.py", "attentions.py", "checkpoint.py", "config.py", "l
 def stage_reference_package(force: bool = False):
     """the model-level checks run the reference's OWN FlowGenerator and
     train_step with `monotonic_align` swapped, on the GPU box -- where /root/reference does not
-    exist.  So the build container stages the package, unmodified, under the git-ignored
-    oracle/_ref/pkg/ (it travels with the snapshot like the compiled kernel; nothing of it enters the
-    repository's history) and puts the reference's compiled OpenMP kernel next to its wrapper.
-    Returns the staged package directory, or None when neither it nor /root/reference exists."""
-    dst = REF_PKG_DIR / "glow_tts_train"
+    exist.  So the build container packs the modules they need, unmodified, together with the
+    reference's compiled OpenMP kernel and a two-line `dataclasses_json` stub (config.py:8 only needs
+    the mixin's name) into ONE archive under the git-ignored oracle/_ref/ (it travels with the snapshot
+    like the compiled kernel; nothing of it enters the repository's history or its working tree as
+    source).  oracle/ref_model.py unpacks it into a temporary directory when a test imports it.
+    Returns the archive's path, or None when neither it nor /root/reference exists."""
+    import zipfile
+
     src = REFERENCE_ROOT / "glow_tts_train"
-    if src.exists() and (force or not all((dst / m).exists() for m in _REF_MODULES)):
-        for m in _REF_MODULES:
-            (dst / m).parent.mkdir(parents=True, exist_ok=True)
-            shutil.copyfile(src / m, dst / m)
-    if not (dst / "models.py").exists():
-        return None
     so = ref_so("omp")
-    if so.exists():
-        target = dst / "monotonic_align" / so.name
-        if not target.exists() or target.stat().st_mtime < so.stat().st_mtime:
-            shutil.copyfile(so, target)
-    stub = REF_PKG_DIR / "dataclasses_json" / "__init__.py"     # config.py:8 only needs the mixin's name
-    if not stub.exists():
-        stub.parent.mkdir(parents=True, exist_ok=True)
-        stub.write_text("class DataClassJsonMixin:\n    pass\n")
-    return dst
+    stale = REF_PKG_ZIP.exists() and so.exists() and REF_PKG_ZIP.stat().st_mtime < so.stat().st_mtime
+    if src.exists() and (force or stale or not REF_PKG_ZIP.exists()):
+        REF_DIR.mkdir(parents=True, exist_ok=True)
+        tmp = REF_PKG_ZIP.with_suffix(".zip.tmp")
+        with zipfile.ZipFile(tmp, "w", zipfile.ZIP_DEFLATED) as z:
+            for m in _REF_MODULES:
+                z.write(src / m, f"glow_tts_train/{m}")
+            if so.exists():
+                z.write(so, f"glow_tts_train/monotonic_align/{so.name}")
+            z.writestr("dataclasses_json/__init__.py", "class DataClassJsonMixin:\n    pass\n")
+        tmp.replace(REF_PKG_ZIP)
+    return REF_PKG_ZIP if REF_PKG_ZIP.exists() else None
 
 
 def build_all(force: bool = False) -> dict:

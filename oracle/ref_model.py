@@ -1,9 +1,9 @@
 """The reference's own model and training step, imported for MODEL-LEVEL checks -- TEST
 INFRASTRUCTURE, NOT PRODUCT CODE (used by tests/, bench.py's `c5` block and profiles/ only).
 
-``import_reference()`` returns the reference's ``glow_tts_train`` package (from oracle/_ref/pkg, where
-oracle/build_ref.py stages it unmodified in the build container; it travels to the GPU box with the
-snapshot).  ``swap_monotonic_align(pkg, module)`` is the two-line drop-in INTEGRATION.md describes:
+``import_reference()`` returns the reference's ``glow_tts_train`` package (unpacked into a temporary
+directory from oracle/_ref/refpkg.zip, where oracle/build_ref.py packs it unmodified in the build
+container; the archive travels to the GPU box with the snapshot).  ``swap_monotonic_align(pkg, module)`` is the two-line drop-in INTEGRATION.md describes:
 ``glow_tts_train.models`` looks ``monotonic_align`` up as a module global at call time
 (models.py:9, :379), so replacing that global replaces the path -- nothing else of the reference
 changes.  ``synthetic_batch`` makes LJSpeech-shaped inputs for ``FlowGenerator.forward`` /
@@ -26,12 +26,19 @@ def import_reference():
     global _pkg
     if _pkg is not None:
         return _pkg
-    pkg_dir = build_ref.stage_reference_package()
-    if pkg_dir is None:
+    archive = build_ref.stage_reference_package()
+    if archive is None:
         return None
-    root = str(pkg_dir.parent)
-    if root not in sys.path:
-        sys.path.insert(0, root)                 # also makes the dataclasses_json stub importable
+    import atexit
+    import shutil
+    import tempfile
+    import zipfile
+
+    root = tempfile.mkdtemp(prefix="mas_refpkg_")   # (the compiled kernel cannot be imported from inside a zip)
+    atexit.register(shutil.rmtree, root, ignore_errors=True)
+    with zipfile.ZipFile(archive) as z:
+        z.extractall(root)
+    sys.path.insert(0, root)                        # also makes the dataclasses_json stub importable
     _pkg = importlib.import_module("glow_tts_train")
     importlib.import_module("glow_tts_train.models")
     importlib.import_module("glow_tts_train.train")

@@ -6,7 +6,7 @@ swapped in -- step time for both, and the share of the step spent inside maximum
     python profiles/c5_train_step.py [--steps 6] [--batch 32] [--t-text 200] [--t-mel 1000]
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 profiles/c5_train_step.py ...
 
-Prints one JSON object (rank 0).  The reference package comes from oracle/_ref/pkg (staged by
+Prints one JSON object (rank 0).  The reference package comes from oracle/_ref/refpkg.zip (packed by
 oracle/build_ref.py in the build container); without it the script reports that and exits 0.
 Synthetic LJSpeech-shaped batches (ragged lengths, one batch per rank: what DistributedSampler
 gives each rank, __main__.py:235); random-init weights."""
@@ -61,7 +61,7 @@ def run(steps=6, warmup=2, batch=32, t_text=200, t_mel=1000, n_speakers=4, gin_c
     rm = importlib.import_module(oracle.__name__ + ".ref_model")
     ref = rm.import_reference()
     if ref is None:
-        return {"unavailable": "reference package not staged under oracle/_ref/pkg"}
+        return {"unavailable": "reference package not staged (oracle/_ref/refpkg.zip)"}
     pkg = entry.load_package()
     train = importlib.import_module(ref.__name__ + ".train")
     theirs = importlib.import_module(ref.__name__ + ".monotonic_align")

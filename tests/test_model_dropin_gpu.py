@@ -1,6 +1,6 @@
 """BASELINE.json configs[4] / SURVEY.md 8d (C5), section 4 test (iv): the drop-in inside the LIVE
 reference model on a B200.  The reference's own FlowGenerator (models.py) and train_step
-(train.py:91-162), staged unmodified under oracle/_ref/pkg by oracle/build_ref.py, run once with
+(train.py:91-162), packed unmodified into oracle/_ref/refpkg.zip by oracle/build_ref.py, run once with
 their own `monotonic_align` (device sync, D2H, the compiled OpenMP Cython kernel, H2D) and once with
 `glow_tts_train.models.monotonic_align` replaced by this repository's module -- the two-line swap of
 INTEGRATION.md.  Same seed, same inputs: the alignment, the durations, the loss and the gradients
@@ -21,7 +21,7 @@ def ref(oracle):
     rm = importlib.import_module(oracle.__name__ + ".ref_model")
     pkg = rm.import_reference()
     if pkg is None:
-        pytest.skip("the reference package was not staged (oracle/_ref/pkg: build in the container that has /root/reference)")
+        pytest.skip("the reference package was not staged (oracle/_ref/refpkg.zip: build in the container that has /root/reference)")
     return rm, pkg
 
 

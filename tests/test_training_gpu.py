@@ -89,7 +89,7 @@ def test_train_step_without_syncs_equals_the_reference_train_step(pkg, oracle):
     rm = importlib.import_module(oracle.__name__ + ".ref_model")
     ref = rm.import_reference()
     if ref is None:
-        pytest.skip("the reference package was not staged (oracle/_ref/pkg)")
+        pytest.skip("the reference package was not staged (oracle/_ref/refpkg.zip)")
     torch.backends.cudnn.deterministic = True
     torch.backends.cudnn.benchmark = False
     train = importlib.import_module(ref.__name__ + ".train")
