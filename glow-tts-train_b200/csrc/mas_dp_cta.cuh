@@ -820,7 +820,11 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 // (blocks + W - 1) steps; what a step costs was measured per R on B200 (32-frame blocks, cycles;
 // `python profiles/measure_step_costs.py` re-measures the table on the device at hand): the in-order warp eats one shuffle latency per frame
 // whatever R is, so two or three tokens per lane cost the same per step and three need fewer warps
-// (less skew); four is an outlier of nvcc's schedule and is only taken when nothing else fits.
+// (less skew); even R cost more than their instruction count says -- lane l reads rows l R .. l R + R - 1 of
+// the TMA box, the hardware's 128-byte swizzle keys a row by (row & 7), so with an even R the eight lanes
+// of a quarter warp share keys and every LDS.128 is a 2- (R = 2, 6) to 8-way (R = 8) bank conflict; R = 4
+// (4-way) is only taken when nothing else fits.  (Kernel (2) writes its score ring itself and keys the
+// rows by their LANE instead: mas_fused.cu, row_key.)
 inline bool choose_shape(int tokens, int &R, int &W) {
     const int groups = ceil_div(tokens, kBlk);         // 32-token groups
     if (groups <= 1) {

@@ -50,7 +50,6 @@ namespace fused {
 
 using systolic::kBlk;
 using systolic::kBndBlocks;
-using systolic::kDoneAll;
 using systolic::kSpinLimit;
 
 constexpr int kThreads = 512;
