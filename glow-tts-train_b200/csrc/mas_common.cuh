@@ -46,4 +46,38 @@ __device__ __forceinline__ Lengths clamp_lengths(int tx, int ty, int T_x, int T_
     return Lengths{tx, ty};
 }
 
+// Exclusive prefix sum of `n` ints (an utterance's durations: the first frame of every token) into
+// shared memory by the whole CTA: every thread sums a contiguous segment, the segment totals are
+// scanned by warp shuffles.  `s_warp`: >= 32 ints of shared scratch.  Ends with a CTA barrier.
+__device__ __forceinline__ void block_exclusive_scan(const int32_t *__restrict__ in, int n, int *s_out, int *s_warp) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + nthr - 1) / nthr, lo = min(n, tid * per), hi = min(n, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += in[i];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < (nthr + 31) / 32 ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        s_warp[lane] = w;                                    // inclusive over the warps
+    }
+    __syncthreads();
+    int run = incl - sum + (warp > 0 ? s_warp[warp - 1] : 0);
+    for (int i = lo; i < hi; ++i) {
+        s_out[i] = run;
+        run += in[i];
+    }
+    __syncthreads();
+}
+
 }  // namespace mas

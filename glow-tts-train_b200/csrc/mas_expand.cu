@@ -33,15 +33,9 @@ __global__ void __launch_bounds__(128) scatter_kernel(const float *__restrict__ 
     extern __shared__ int s_start[];                      // exclusive prefix sum of the durations of this utterance
     const int b = blockIdx.z, d = blockIdx.y;
     const int32_t *du = dur + (int64_t)b * T_x;
-    // every CTA recomputes the prefix (T_x <= 2048 ints): cheap next to the frame traffic
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int x = 0; x < T_x; ++x) {
-            s_start[x] = run;
-            run += du[x];
-        }
-    }
-    __syncthreads();
+    // every CTA recomputes the prefix (T_x <= 2048 ints), in parallel: cheap next to the frame traffic
+    __shared__ int s_warp[32];
+    block_exclusive_scan(du, T_x, s_start, s_warp);
     const int x = blockIdx.x * 128 + threadIdx.x;
     if (x >= T_x) return;
     const int n = du[x], y0 = s_start[x];

@@ -101,14 +101,8 @@ __global__ void __launch_bounds__(128) mle_grad_tokens_kernel(const float *__res
     extern __shared__ int s_start[];                      // exclusive prefix sum of this utterance's durations
     const int b = blockIdx.z, d = blockIdx.y;
     const int32_t *du = dur + (int64_t)b * T_x;
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int x = 0; x < T_x; ++x) {
-            s_start[x] = run;
-            run += du[x];
-        }
-    }
-    __syncthreads();
+    __shared__ int s_warp[32];
+    block_exclusive_scan(du, T_x, s_start, s_warp);
     const int x = blockIdx.x * 128 + threadIdx.x;
     if (x >= T_x) return;
     const int64_t row = (int64_t)b * D + d;
