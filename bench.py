@@ -299,6 +299,34 @@ class Timer:
         return graph, keep, statistics.median(times), min(times), times
 
 
+def numa_local_affinity(dev):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that the pinned host
+    buffers of the end-to-end loop are allocated there.  Returns what was found; "restore" = the affinity
+    to put back afterwards (the CPU baseline uses every core)."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        props = torch.cuda.get_device_properties(dev)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int((Path("/sys/bus/pci/devices") / bdf / "numa_node").read_text())
+        info["pci"] = bdf
+        if node < 0:
+            return info
+        cpus = set()
+        for part in (Path(f"/sys/devices/system/node/node{node}/cpulist")).read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info["numa_node"] = node
+        if use:
+            info["restore"] = allowed
+            os.sched_setaffinity(0, use)
+            info["cpus"] = len(use)
+    except (OSError, ValueError, AttributeError):
+        pass
+    return info
+
+
 def fp32_peak_tflops(dev, clocks):
     """CUDA-core FMA peak, derived: SMs x 128 lanes x 2 flop x the SM clock's maximum."""
     props = torch.cuda.get_device_properties(dev)
@@ -424,6 +452,9 @@ def run_ours(args):
     # streams (triple-buffered pinned results), the way a host loop that feeds the GPU would be
     # written: step i's D2H overlaps step i+1's H2D and kernels (separate copy engines).
     n_lanes = 3
+    # pinned buffers first-touched from the CPUs of the GPU's own NUMA node (N > 1: eight ranks' copies
+    # otherwise cross the socket interconnect on their way to the PCIe root)
+    host_info = numa_local_affinity(dev)
     host = [drop_logs(tuple(t.pin_memory() for t in synth_inputs(B, D, T_x, T_y, SEED + 77 + rank * 1000 + i, mean_only)))
             for i in range(n_lanes)]
     host_out = [torch.empty((B, T_x, T_y), dtype=torch.float32).pin_memory() for _ in range(n_lanes)]
@@ -477,6 +508,8 @@ def run_ours(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     e2e_ms, e2e_compact_ms = times.tolist()
     del host_out, host_dur, host
+    if host_info.get("restore") is not None:
+        os.sched_setaffinity(0, host_info.pop("restore"))
     value = world * cells * args.steps / (dev_ms * 1e-3)
     e2e_value = world * cells * e2e_steps / (e2e_ms * 1e-3)
 
@@ -609,6 +642,7 @@ def run_ours(args):
                     "h2d_gb_per_s_all_gpus": world * in_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9,
                     "d2h_gb_per_s_all_gpus": world * out_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9,
                     "pipeline": "3 streams, triple-buffered pinned results; each step: H2D inputs, fused call, D2H dense path + durations",
+                    "host": {k: v for k, v in host_info.items() if k != "restore"},
                     "durations_only": {"value": world * cells * e2e_steps / (e2e_compact_ms * 1e-3), "unit": UNIT,
                                        "d2h_bytes_per_step": B * T_x * 4, "ms_per_step": e2e_compact_ms / e2e_steps,
                                        "what": "same loop, the dense path stays on the device (its consumers run there); "
