@@ -58,7 +58,7 @@ constexpr int kStages = 3;             // z panels in flight per team
 constexpr int kZeroPage = 8192;        // bytes of zeros the dense output is filled from
 constexpr int kMaxTeams = 8;
 constexpr int kBarFfma = 15;           // named barrier of all FFMA threads; teams use 1 .. nteams
-constexpr int kBarSums = 14;           // ... of the warps that sum the row constants
+constexpr int kBarAll = 14;            // ... and the sweep warp (operand hand-over, row constants ready)
 constexpr int kMaxClusters = 192;      // workspace bound (no device query in the size function)
 
 // control words in shared memory (ints)
@@ -169,38 +169,46 @@ __device__ __forceinline__ void stage_ops(const Geom &g, const Utt &u, const Log
             if (x >= TR) x -= TR;
         }
     }
-    named_sync(kBarFfma, nffma);
     if (dbg && fidx == 0) dbg[27] = ptx::globaltimer_ns();
-    // The row constants are not needed before the first chunk is finished (a whole contraction pass
-    // away): only the warps that sum them stay; the others start contracting.  (team_contract meets
-    // them at the FFMA barrier before its first store.)
-    const int sum_threads = ((g.nsh * TR + 31) & ~31) < nffma ? ((g.nsh * TR + 31) & ~31) : nffma;
-    if (fidx >= sum_threads) return;
-    if (fidx < g.nsh * TR) {
-        const int h = fidx / TR, x = fidx - h * TR;
+    named_sync(kBarAll, nffma + 32);                       // the raw values are parked: the sweep warp sums the row constants
+}
+
+// The row constants l1, l4 of the slice's tokens, summed the way mas_logp_cta.cuh::stage_tokens does (nsh
+// shares of dsh channels, ascending inside a share, shares added in order: bit-identical) from what
+// stage_ops left in the ring.  By the SWEEP warp: it has nothing to sweep before the first chunk is
+// stored a whole contraction pass later, the FFMA warps start contracting at once, and both meet
+// at the barrier before the first store (team_contract).
+__device__ __forceinline__ void sum_row_constants(const Geom &g, const Utt &u, const LogpParams &p, unsigned char *smem, int lane) {
+    const int D = p.D, TR = u.TR;
+    float *sL1 = reinterpret_cast<float *>(smem + g.off_l14), *sL4 = sL1 + g.tr_max;
+    float *sPart = reinterpret_cast<float *>(smem + g.off_part);
+    const float *tM = reinterpret_cast<const float *>(smem + g.off_ring), *tL = tM + D * TR, *tR = tL + D * TR;   // -0.5 m^2, logs, exp(-2 logs)
+    const bool has_logs = p.x_logs != nullptr;
+    for (int pair = lane; pair < g.nsh * TR; pair += 32) {
+        const int h = pair / TR, x = pair - h * TR;
         const int d0 = h * g.dsh, d1 = min(D, d0 + g.dsh);
         float l1 = 0.f, l4 = 0.f;
         if (x < u.n_real) {
 #pragma unroll 8
             for (int d = d0; d < d1; ++d) {
-                const float ls = xl ? tL[d * TR + x] : 0.f;
+                const float ls = has_logs ? tL[d * TR + x] : 0.f;
                 l1 += kNegHalfLog2Pi - ls;                          // models.py:364-366
-                const float r = !xl ? 1.0f : g.ops_tmp3 ? tR[d * TR + x] : expf(-2.0f * ls);   // (no room: the same expression again)
+                const float r = !has_logs ? 1.0f : g.ops_tmp3 ? tR[d * TR + x] : expf(-2.0f * ls);   // (no room: the same expression again)
                 l4 = fmaf(tM[d * TR + x], r, l4);                   // models.py:373-375: -0.5 m^2 exp(-2 logs)
             }
         }
         sPart[(2 * h) * TR + x] = l1;
         sPart[(2 * h + 1) * TR + x] = l4;
     }
-    named_sync(kBarSums, sum_threads);
-    if (fidx < TR) {
-        float l1 = sPart[fidx], l4 = sPart[TR + fidx];
+    __syncwarp();
+    for (int x = lane; x < TR; x += 32) {
+        float l1 = sPart[x], l4 = sPart[TR + x];
         for (int h = 1; h < g.nsh; ++h) {
-            l1 += sPart[(2 * h) * TR + fidx];
-            l4 += sPart[(2 * h + 1) * TR + fidx];
+            l1 += sPart[(2 * h) * TR + x];
+            l4 += sPart[(2 * h + 1) * TR + x];
         }
-        sL1[fidx] = l1;
-        sL4[fidx] = l4;
+        sL1[x] = l1;
+        sL4[x] = l4;
     }
 }
 
@@ -220,7 +228,7 @@ template <bool kMeanOnly>
 __device__ __forceinline__ int team_contract(const CUtensorMap &tmap_z, const Geom &g, const Utt &u, const LogpParams &p,
                                              unsigned char *smem, int *ctl, int team, int ttid, int tn, int seq0, bool prologue) {
     if (team >= u.nch) {                                    // more teams than chunks
-        if (!prologue) named_sync(kBarFfma, g.nteams * tn);   // (the barrier the others pass before their first store)
+        if (!prologue) named_sync(kBarAll, g.nteams * tn + 32);   // (the barrier the others pass before their first store)
         return seq0;
     }
     const int D = p.D, F = u.F, CG = u.CG, TR = u.TR, NB = g.NB;
@@ -306,7 +314,7 @@ __device__ __forceinline__ int team_contract(const CUtensorMap &tmap_z, const Ge
         }
         float *sL2 = sL2_base + (count & 1) * g.F_cap;
         if (kMeanOnly && ttid < F) sL2[ttid] = l2;
-        if (count == 0) named_sync(kBarFfma, g.nteams * tn);   // the row constants are summed (stage_ops)
+        if (count == 0) named_sync(kBarAll, g.nteams * tn + 32);   // the sweep warp has summed the row constants
         named_sync(bar, tn);                                // the ring has room (and the frame sums are there)
         if (worker) {
             const int fb = u.f_lo + j * F;                  // the chunk's first frame
@@ -404,11 +412,7 @@ template <int R, bool kDbg>
 __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned char *smem, int *ctl, float neg, ZeroFill &zf,
                                            uint32_t *bits_g, long long *dbg) {
     const int lane = threadIdx.x & 31;
-    const void *zero_page = smem + g.off_zero;
     int nonfinite = 0;
-    // the dense output's zeros: all bulk copies now, while the sweep has nothing to do yet (the first
-    // chunk of scores is a whole contraction pass away); they drain in the background
-    if (lane == 0) zf.drip(zero_page, 0x7fffffff);
     long long t_chunks = 0, t_prev = 0, t_credit = 0, t_core = 0, t_bits = 0, t_done = 0, t_fill = 0, t_begin = 0, t_core_tail = 0, t_all_tail = 0;
     if (kDbg) t_begin = clock64();
     if (u.cbend >= u.cb0) {
@@ -835,11 +839,19 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
             zf.off = 0;
             zf.per_block = ceil_div((int)((zf.total + kZeroPage - 1) / kZeroPage), max(1, u.cbend - u.cb0 + 1));
             uint32_t *bits_g = g.bits_in_smem ? nullptr : g.ws_bits + ((size_t)cluster_id * K + c) * g.nblk * g.ring_rows;
+            // the dense output's zeros: all bulk copies now, while the sweep has nothing to do yet (the first
+            // chunk of scores is a whole contraction pass away); they drain in the background
+            if (lane == 0) zf.drip(smem + g.off_zero, 0x7fffffff);
+            if (active) {
+                named_sync(kBarAll, g.nteams * tn + 32);    // stage_ops has parked the raw token-side values
+                sum_row_constants(g, u, lp, smem, lane);
+                if (kDbg && dbg && lane == 0) dbg[1] = ptx::globaltimer_ns();
+                named_sync(kBarAll, g.nteams * tn + 32);    // (the teams wait here before their first store)
+            }
             nonfinite = sweep_slice<R, kDbg>(g, u, smem, ctl, neg, zf, bits_g, dbg);
         } else if (in_team && active) {
             team_contract<false>(tmap_z, g, u, lp, smem, ctl, team, ttid, tn, zseq, true);
             stage_ops(g, u, lp, smem, fidx, g.nteams * tn, kDbg ? dbg : nullptr);
-            if (kDbg && dbg && fidx == 0) dbg[1] = ptx::globaltimer_ns();
             if (lp.x_logs == nullptr)
                 zseq = team_contract<true>(tmap_z, g, u, lp, smem, ctl, team, ttid, tn, zseq, false);
             else
