@@ -41,6 +41,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "mas_dp_cta.cuh"
 #include "mas_logp_cta.cuh"
@@ -78,10 +79,11 @@ struct Geom {
     int nblk, bits_in_smem;
     int ops_tmp3;                      // the ring has room for stage_ops' third scratch array (exp(-2 logs))
     int use_maps;                      // build the backtrack's block maps while the sweep runs (short slices only)
+    int use_exit;                      // ... and with them the exit table (build_block_maps)
     int passes;                        // contraction passes of a full-length utterance (host estimate)
     int nsh, dsh;                      // channel shares of the row constants, as the materialising kernel sums them
     int off_zero, off_bnd, off_run, off_xend, off_ctl, off_bar, off_big, off_ops, off_l14, off_part, off_z, off_l2, off_ring, off_bits,
-        off_maps, total;
+        off_maps, off_exit, off_erow, total;
     uint32_t *ws_bits;                 // [NC][K][nblk][ring_rows] when the bits do not fit shared memory
     unsigned char *ws_maps;            // ... and the backtrack's block maps [NC][K][nblk][ring_rows] bytes with them
     float *redo_scratch;               // [NC][T_x][t_ref.F]
@@ -123,6 +125,9 @@ __device__ __forceinline__ void st_release_shared(int *p, int v) { ptx::st_relea
 // all threads, the row constants summed the way mas_logp_cta.cuh::stage_tokens does (nsh shares of
 // dsh channels, ascending inside a share, shares added in order) from the same expressions, so
 // that they are bit-identical.
+// kIssue: only the copies are issued (before the utterance's cluster barrier: nothing of the previous
+// utterance is left in the ring after its last barrier, and the copies fly while this one is passed).
+template <bool kIssue>
 __device__ __forceinline__ void stage_ops(const Geom &g, const Utt &u, const LogpParams &p, unsigned char *smem, int fidx, int nffma,
                                           long long *dbg) {
     const int D = p.D, T_x = p.T_x, TR = u.TR;
@@ -136,7 +141,7 @@ __device__ __forceinline__ void stage_ops(const Geom &g, const Utt &u, const Log
     const int total = D * TR;
     // element e = fidx + k nffma is (channel d, token x): stepped without a division per element
     const int d_first = fidx / TR, x_first = fidx - d_first * TR, d_step = nffma / TR, x_step = nffma - d_step * TR;
-    {
+    if (kIssue) {
         int d = d_first, x = x_first;
         for (int e = fidx; e < total; e += nffma) {
             if (x < u.n_real) {
@@ -146,8 +151,9 @@ __device__ __forceinline__ void stage_ops(const Geom &g, const Utt &u, const Log
             d += d_step, x += x_step;
             if (x >= TR) x -= TR, ++d;
         }
+        ptx::cp_async_commit();
+        return;
     }
-    ptx::cp_async_commit();
     ptx::cp_async_wait<0>();
     named_sync(kBarFfma, nffma);
     if (dbg && fidx == 0) dbg[26] = ptx::globaltimer_ns();
@@ -657,21 +663,61 @@ __device__ __forceinline__ int walk_block_warp(const uint32_t *row, int xl, int 
     return xl;
 }
 
-// Block maps of this CTA's slice for blocks cbl = first, first + step, ... as the sweep finishes them.
+// walk_block that also reports where the path stepped onto the slice's FIRST token (y0), if it did.
 template <bool kSmem>
-__device__ __forceinline__ void build_block_maps(const Geom &g, const Utt &u, const uint32_t *bits, unsigned char *maps, const int *ctl,
-                                                 int first, int step, int lane) {
+__device__ __forceinline__ int walk_block_exit(const uint32_t *row, int xl, int y, int x0, int col0, int &y0) {
+    while (xl >= 0 && x0 + xl > 0) {
+        const uint32_t w = (kSmem ? row[xl] : __ldcg(row + xl)) & (0xffffffffu >> (31 - y));
+        if (w == 0u) break;
+        const int lo = 31 - __clz(w);
+        if (xl == 0) y0 = col0 + lo;
+        --xl;
+        if (lo == 0) break;
+        y = lo - 1;
+    }
+    return xl;
+}
+
+// Block maps of this CTA's slice as the sweep finishes the blocks.  A unit is (block, 32 tokens); the
+// builder warps take units first, first + step, ...: the groups of one block go to different warps, so
+// that the maps of the slice's last blocks -- the only ones on the critical path, between the end of the
+// sweep and the backtrack -- are there one walk after the sweep, not one walk per group.
+//
+// EXIT TABLE (`exits` != nullptr: CTAs 1 .. K-1): exits[block][token] = the frame where the path steps onto
+// the slice's first token when it is on `token` at the block's last frame -- the composition of all the
+// maps below, tabulated: exits[b][x] = exits[b-1][x - map[b][x]], or the frame the walk itself found when
+// the path leaves the slice inside block b.  A row needs the row below complete (`erow` counts a row's
+// finished groups; units are taken in ascending order, so the wait is always for a unit that is done or
+// in progress).  The backtrack's hop through this CTA is then the entry block's walk and ONE look-up
+// before the hand-over to the CTA below, instead of a dependent load per block in between.
+template <bool kSmem>
+__device__ __forceinline__ void build_block_maps(const Geom &g, const Utt &u, const uint32_t *bits, unsigned char *maps,
+                                                 unsigned short *exits, int *erow, const int *ctl, int first, int step, int lane) {
     const int nbox = u.cbend - u.cb0;                       // (not the last block: a path only ever ENTERS a slice there)
+    const int ngrp = ceil_div(u.n_real, 32);
     uint32_t spins = 0;
-    for (int cbl = first; cbl < nbox; cbl += step) {
+    for (int unit = first; unit < nbox * ngrp; unit += step) {
+        const int cbl = unit / ngrp, xl = (unit - cbl * ngrp) * 32 + lane;
         while (ld_acquire_shared(ctl + kConsumed) <= cbl) {
-            __nanosleep(400);
+            __nanosleep(cbl + 3 >= nbox ? 50 : 400);
             if (++spins > kSpinLimit) systolic::spin_fail();
         }
-        const uint32_t *row = bits + (size_t)(u.cb0 + cbl) * g.ring_rows;
-        for (int xl = lane; xl < u.n_real; xl += 32) {
-            const int r = walk_block<kSmem, false>(row, xl, 31, u.x0, 0, nullptr);
+        int r = -1, y0 = 0;
+        if (xl < u.n_real) {
+            const uint32_t *row = bits + (size_t)(u.cb0 + cbl) * g.ring_rows;
+            r = walk_block_exit<kSmem>(row, xl, 31, u.x0, (u.cb0 + cbl) * kBlk, y0);
             maps[(size_t)cbl * g.ring_rows + xl] = (unsigned char)(r < 0 ? kLeft : xl - r);
+        }
+        if (exits != nullptr) {
+            if (cbl > 0)
+                while (ld_acquire_shared(erow + cbl - 1) < ngrp) {
+                    __nanosleep(20);
+                    if (++spins > kSpinLimit) systolic::spin_fail();
+                }
+            // (in the slice's first block every walk leaves the slice: the path is on a token <= its frame)
+            if (xl < u.n_real) exits[cbl * g.ring_rows + xl] = (unsigned short)(r < 0 ? y0 : exits[(cbl - 1) * g.ring_rows + r]);
+            __syncwarp();
+            if (lane == 0) ptx::red_release_shared_add(erow + cbl, 1);
         }
     }
 }
@@ -743,6 +789,8 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
     int *xend = reinterpret_cast<int *>(smem + g.off_xend);       // token at the last frame of each block of the slice (-1: not composed)
     uint32_t *bits_s = reinterpret_cast<uint32_t *>(smem + g.off_bits);
     unsigned char *maps_s = smem + g.off_maps;
+    unsigned short *exits_s = reinterpret_cast<unsigned short *>(smem + g.off_exit);
+    int *erow = reinterpret_cast<int *>(smem + g.off_erow);
     const float neg = pp.max_neg_val;
 
     // FFMA role: every warp but the sweep warp, or only those on the other three schedulers
@@ -826,8 +874,16 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
             ptx::fence_barrier_init();
             ptx::mbar_arrive_expect_tx(bnd_bars + kBndBlocks, 8);
         }
-        for (int i = tid; i <= u.cbend - u.cb0; i += kThreads) xend[i] = -1;
+        for (int i = tid; i <= u.cbend - u.cb0; i += kThreads) {
+            xend[i] = -1;
+            if (g.use_exit) erow[i] = 0;
+        }
         if (kDbg && dbg && tid == 0) dbg[0] = ptx::globaltimer_ns();
+        if (in_team && active) {
+            // the first z panels and the raw token-side values: issued before the barrier, they land meanwhile
+            team_contract<false>(tmap_z, g, u, lp, smem, ctl, team, ttid, tn, zseq, true);
+            stage_ops<true>(g, u, lp, smem, fidx, g.nteams * tn, nullptr);
+        }
         ptx::cluster_sync();
 
         int nonfinite = 0;
@@ -850,8 +906,7 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
             }
             nonfinite = sweep_slice<R, kDbg>(g, u, smem, ctl, neg, zf, bits_g, dbg);
         } else if (in_team && active) {
-            team_contract<false>(tmap_z, g, u, lp, smem, ctl, team, ttid, tn, zseq, true);
-            stage_ops(g, u, lp, smem, fidx, g.nteams * tn, kDbg ? dbg : nullptr);
+            stage_ops<false>(g, u, lp, smem, fidx, g.nteams * tn, kDbg ? dbg : nullptr);
             if (lp.x_logs == nullptr)
                 zseq = team_contract<true>(tmap_z, g, u, lp, smem, ctl, team, ttid, tn, zseq, false);
             else
@@ -864,17 +919,24 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
             // the warps on the other three schedulers, once their contraction is done: the backtrack's block maps
             const int bw = (warp - 1) - (warp >> 2);
             if (g.bits_in_smem)
-                build_block_maps<true>(g, u, bits_s, maps, ctl, bw, 12, lane);
+                build_block_maps<true>(g, u, bits_s, maps, (g.use_exit && c > 0) ? exits_s : nullptr, erow, ctl, bw, 12, lane);
             else
-                build_block_maps<false>(g, u, bits_w, maps, ctl, bw, 12, lane);
+                build_block_maps<false>(g, u, bits_w, maps, nullptr, erow, ctl, bw, 12, lane);
+            if (kDbg && dbg && warp == 1 && lane == 0) dbg[3] = ptx::globaltimer_ns();
         }
         if (!g.bits_in_smem) __threadfence();
 
         // ---- were all scores finite?  (cluster-wide) ----
         const int any_bad = __syncthreads_or(nonfinite);
-        if (any_bad && tid == 0)
+        if (kDbg && dbg && tid == 0) dbg[2] = ptx::globaltimer_ns();
+        // The only thing this barrier carries across the cluster is the redo flag, so only a CTA that raises
+        // it pays for a release (a fence at cluster scope is a MEMBAR.ALL.GPU: ~1 us on the critical path
+        // between the last sweep and the backtrack); everybody else arrives relaxed.
+        if (any_bad && tid == 0) {
             for (int r = 0; r < K; ++r) ptx::st_cluster_u32(ptx::mapa(ptx::smem_u32(ctl + kRedo), (uint32_t)r), 1u);
-        ptx::cluster_sync();
+            ptx::fence_acq_rel_cluster();
+        }
+        ptx::cluster_sync_arrive_relaxed();
         const bool redo = vctl[kRedo] != 0;
         const uint32_t *bits_gl = g.bits_in_smem ? nullptr : g.ws_bits + ((size_t)cluster_id * K + c) * g.nblk * g.ring_rows;
         int bits_rows = g.ring_rows;
@@ -941,69 +1003,89 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
                 if (pp.durations) pp.durations[(int64_t)b * T_x + x] = r.y - r.x + 1;
             }
         } else {
-            const uint32_t *bits_b = g.bits_in_smem ? bits_s : bits_w;
-            if (warp == 0 && c <= c_last) {
-                // (the whole sweep warp, uniformly) compose the block maps from the entry point down; walk only
-                // the entry block and the block where the path leaves the slice
-                int xl, y;
-                if (c == c_last) {
-                    xl = u.tx - 1 - u.x0;
-                    y = u.ty - 1;
-                } else {
-                    uint32_t spins = 0;
-                    while (!ptx::mbar_try_wait_a(bt_bar_a, 0u))
-                        if (++spins > kSpinLimit) systolic::spin_fail();
-                    xl = vctl[kBtToken] - u.x0;
-                    y = vctl[kBtFrame];
-                }
-                const long long tb0 = kDbg ? clock64() : 0;
-                if (lane == 0) ylo[xl + 1] = y + 1;         // where the token above begins
-                int cb = y >> 5;
-                const uint32_t *row = bits_b + (size_t)cb * g.ring_rows;
-                xl = g.bits_in_smem ? walk_block_warp<true, true>(row, xl, y & 31, u.x0, cb * kBlk, ylo, lane)
-                                    : walk_block_warp<false, true>(row, xl, y & 31, u.x0, cb * kBlk, ylo, lane);
-                const long long tb1 = kDbg ? clock64() : 0;
-                int nsteps = 0;
-                while (xl >= 0 && --cb >= u.cb0) {
-                    ++nsteps;
-                    // (every map below a slice's last block is complete: its builders passed the CTA barrier above;
-                    // the last block is only ever an entry block, walked directly, and nobody builds its map)
-                    const int m = maps[(size_t)(cb - u.cb0) * g.ring_rows + xl];
-                    if (m == kLeft) {                       // the path leaves the slice here
-                        row = bits_b + (size_t)cb * g.ring_rows;
-                        xl = g.bits_in_smem ? walk_block_warp<true, true>(row, xl, 31, u.x0, cb * kBlk, ylo, lane)
-                                            : walk_block_warp<false, true>(row, xl, 31, u.x0, cb * kBlk, ylo, lane);
-                        continue;
-                    }
-                    if (lane == 0) xend[cb - u.cb0] = xl;
-                    xl -= m;
-                }
-                __syncwarp();
-                if (kDbg && dbg && lane == 0) dbg[30] = tb1 - tb0, dbg[31] = clock64() - tb1, dbg[25] = nsteps;
-                if (lane == 0) {
-                    if (c == 0) {
-                        ylo[0] = 0;
+            // (one instantiation per place the direction words and maps live in: with the pointers selected at
+            // run time every load of the composition and of the walks was a generic LD -- ~260 cycles per
+            // composed block on the backtrack's critical path instead of a shared-memory load's ~50)
+            auto backtrack_by_maps = [&](auto in_smem) {
+                constexpr bool kS = decltype(in_smem)::value;
+                const uint32_t *bits_b = kS ? bits_s : bits_w;
+                const unsigned char *maps_b = kS ? maps_s : maps;
+                const uint32_t maps_a = kS ? ptx::smem_u32(maps_s) : 0u;
+                if (warp == 0 && c <= c_last) {
+                    // (the whole sweep warp, uniformly) compose the block maps from the entry point down; walk only
+                    // the entry block and the block where the path leaves the slice
+                    int xl, y;
+                    if (c == c_last) {
+                        xl = u.tx - 1 - u.x0;
+                        y = u.ty - 1;
                     } else {
-                        ptx::st_async_b64(ptx::mapa(ptx::smem_u32(ctl + kBtToken), (uint32_t)(c - 1)),
-                                          (uint64_t)(uint32_t)(u.x0 - 1) | ((uint64_t)(uint32_t)(ylo[0] - 1) << 32),
-                                          ptx::mapa(bt_bar_a, (uint32_t)(c - 1)));
+                        uint32_t spins = 0;
+                        while (!ptx::mbar_try_wait_a(bt_bar_a, 0u))
+                            if (++spins > kSpinLimit) systolic::spin_fail();
+                        xl = vctl[kBtToken] - u.x0;
+                        y = vctl[kBtFrame];
+                    }
+                    const long long tb0 = kDbg ? clock64() : 0;
+                    if (lane == 0) ylo[xl + 1] = y + 1;         // where the token above begins
+                    int cb = y >> 5;
+                    xl = walk_block_warp<kS, true>(bits_b + (size_t)cb * g.ring_rows, xl, y & 31, u.x0, cb * kBlk, ylo, lane);
+                    const long long tb1 = kDbg ? clock64() : 0;
+                    // the hand-over to the CTA below, as early as it is known: (token, frame) just before the path
+                    // steps onto this slice's first token
+                    const uint32_t peer_tok = c > 0 ? ptx::mapa(ptx::smem_u32(ctl + kBtToken), (uint32_t)(c - 1)) : 0u;   // (8-byte aligned)
+                    const uint32_t peer_bar = c > 0 ? ptx::mapa(bt_bar_a, (uint32_t)(c - 1)) : 0u;
+                    bool sent = false;
+                    if (c > 0 && lane == 0) {
+                        int y0 = -1;
+                        if (xl < 0)
+                            y0 = ylo[0];                        // it left the slice inside the entry block
+                        else if (kS && g.use_exit && cb - 1 >= u.cb0)
+                            y0 = exits_s[(cb - 1 - u.cb0) * g.ring_rows + xl];
+                        if (y0 >= 0) {
+                            ptx::st_async_b64(peer_tok, (uint64_t)(uint32_t)(u.x0 - 1) | ((uint64_t)(uint32_t)(y0 - 1) << 32), peer_bar);
+                            sent = true;
+                        }
+                    }
+                    if (kDbg && dbg && lane == 0) dbg[13] = ptx::globaltimer_ns();
+                    int nsteps = 0;
+                    int row_off = (cb - u.cb0) * g.ring_rows;
+                    while (xl >= 0 && --cb >= u.cb0) {
+                        ++nsteps;
+                        row_off -= g.ring_rows;
+                        // (every map below a slice's last block is complete: its builders passed the CTA barrier above;
+                        // the last block is only ever an entry block, walked directly, and nobody builds its map)
+                        const int m = kS ? (int)ptx::ld_shared_u8_a(maps_a + (uint32_t)(row_off + xl)) : (int)maps_b[row_off + xl];
+                        if (m == kLeft) {                       // the path leaves the slice here
+                            xl = walk_block_warp<kS, true>(bits_b + (size_t)cb * g.ring_rows, xl, 31, u.x0, cb * kBlk, ylo, lane);
+                            continue;
+                        }
+                        if (lane == 0) xend[cb - u.cb0] = xl;
+                        xl -= m;
+                    }
+                    __syncwarp();
+                    if (kDbg && dbg && lane == 0) dbg[30] = tb1 - tb0, dbg[31] = clock64() - tb1, dbg[25] = nsteps;
+                    if (lane == 0) {
+                        if (c == 0)
+                            ylo[0] = 0;
+                        else if (!sent)
+                            ptx::st_async_b64(peer_tok, (uint64_t)(uint32_t)(u.x0 - 1) | ((uint64_t)(uint32_t)(ylo[0] - 1) << 32), peer_bar);
                     }
                 }
-            }
-            __syncthreads();
-            if (kDbg && dbg && tid == 0) dbg[6] = ptx::globaltimer_ns();
-            // one warp per composed block: the frames where the path steps onto the tokens it visits there
-            if (c <= c_last) {
-                for (int cbl = warp; cbl <= u.cbend - u.cb0; cbl += kThreads / 32) {
-                    const int xe = xend[cbl];
-                    if (xe < 0) continue;
-                    const uint32_t *row = bits_b + (size_t)(u.cb0 + cbl) * g.ring_rows;
-                    if (g.bits_in_smem)
-                        walk_block_warp<true, true>(row, xe, 31, u.x0, (u.cb0 + cbl) * kBlk, ylo, lane);
-                    else
-                        walk_block_warp<false, true>(row, xe, 31, u.x0, (u.cb0 + cbl) * kBlk, ylo, lane);
+                __syncthreads();
+                if (kDbg && dbg && tid == 0) dbg[6] = ptx::globaltimer_ns();
+                // one warp per composed block: the frames where the path steps onto the tokens it visits there
+                if (c <= c_last) {
+                    for (int cbl = warp; cbl <= u.cbend - u.cb0; cbl += kThreads / 32) {
+                        const int xe = xend[cbl];
+                        if (xe < 0) continue;
+                        walk_block_warp<kS, true>(bits_b + (size_t)(u.cb0 + cbl) * g.ring_rows, xe, 31, u.x0, (u.cb0 + cbl) * kBlk, ylo, lane);
+                    }
                 }
-            }
+            };
+            if (g.bits_in_smem)
+                backtrack_by_maps(std::true_type{});
+            else
+                backtrack_by_maps(std::false_type{});
             __syncthreads();
             // ---- dense path: ones, durations, frame -> token ----
             for (int xl = tid; xl < u.n_real; xl += kThreads) {
@@ -1064,7 +1146,12 @@ static bool layout_geom(int D, int T_x, int max_smem, Geom &g) {
     // flight it never stalls them; stage_ops parks the raw token-side values in it (2 arrays at least)
     int nb_floor = ceil_div(g.F_cap + 2 * kBlk, kBlk);
     if (nb_floor * box < 2 * D * g.tr_max * 4) nb_floor = ceil_div(2 * D * g.tr_max * 4, box);
-    const int bits_bytes = g.nblk * g.ring_rows * 5;       // direction words + one map byte per token and block
+    static const char *maps_env = getenv("MAS_B200_FUSED_MAPS");           // experiment hooks
+    static const char *exit_env = getenv("MAS_B200_FUSED_EXIT");
+    const bool want_maps = maps_env ? atoi(maps_env) != 0 : g.max_slice <= 64;
+    const bool want_exit = want_maps && g.nblk * kBlk < 65536 && (exit_env ? atoi(exit_env) != 0 : true);
+    // direction words + one map byte per token and block (+ the exit table: two bytes each, and a counter per block)
+    const int bits_bytes = g.nblk * g.ring_rows * 5 + (want_exit ? g.nblk * g.ring_rows * 2 + g.nblk * 4 : 0);
     const int redo_need = g.off_big + (logp::cta_smem_floats(D, g.t_ref) - D * g.t_ref.F) * 4 + 2 * T_x * 4 + 16;   // (redo_utterance)
     if (redo_need > max_smem) return false;
     for (int bits_smem = 1; bits_smem >= 0; --bits_smem) {
@@ -1079,10 +1166,12 @@ static bool layout_geom(int D, int T_x, int max_smem, Geom &g) {
             g.NB = nb;
             g.bits_in_smem = bits_smem;
             g.ops_tmp3 = (int64_t)nb * box >= (int64_t)3 * D * g.tr_max * 4;
-            static const char *maps_env = getenv("MAS_B200_FUSED_MAPS");           // experiment hook
-            g.use_maps = maps_env ? atoi(maps_env) != 0 && bits_smem : (bits_smem && g.max_slice <= 64);
+            g.use_maps = want_maps && bits_smem;
+            g.use_exit = want_exit && bits_smem;
             g.off_bits = g.off_ring + nb * box;
             g.off_maps = g.off_bits + g.nblk * g.ring_rows * 4;
+            g.off_exit = g.off_maps + g.nblk * g.ring_rows;        // (ring_rows is a multiple of 8: 2-byte aligned, then 4-byte aligned)
+            g.off_erow = g.off_exit + g.nblk * g.ring_rows * 2;
             g.total = g.off_bits + (bits_smem ? bits_bytes : 0);
             if (g.total < redo_need) g.total = redo_need;
             return true;

@@ -61,6 +61,11 @@ __device__ __forceinline__ void st_release_shared_if_a(bool pred, uint32_t addr,
 __device__ __forceinline__ void st_shared_u32_a(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_shared_u8_a(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ float ld_shared_f32_a(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -177,6 +182,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     return r;
 }
 // every thread of every CTA of the cluster; release/acquire at cluster scope
+// arrive without a release + wait: for a barrier whose arrivals publish nothing (a CTA that does
+// publish fences first, fence_acq_rel_cluster)
+__device__ __forceinline__ void cluster_sync_arrive_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
