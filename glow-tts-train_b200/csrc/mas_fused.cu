@@ -596,6 +596,7 @@ __device__ __forceinline__ int sweep_slice(const Geom &g, const Utt &u, unsigned
             ptx::bulk_commit_group();
             ptx::bulk_wait_all();                          // the ones are written after the next barriers
         }
+        if (kDbg && dbg) dbg[14] = ptx::globaltimer_ns();
     }
     __syncwarp();
     return nonfinite;
@@ -923,6 +924,7 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
             else
                 build_block_maps<false>(g, u, bits_w, maps, nullptr, erow, ctl, bw, 12, lane);
             if (kDbg && dbg && warp == 1 && lane == 0) dbg[3] = ptx::globaltimer_ns();
+            if (kDbg && dbg && lane == 0) atomicMax(reinterpret_cast<unsigned long long *>(dbg + 15), (unsigned long long)ptx::globaltimer_ns());
         }
         if (!g.bits_in_smem) __threadfence();
 

@@ -51,7 +51,7 @@ for c in range(K):
         return (np.median(col - t0) / 1e3, (col.max() - t0) / 1e3) if len(col) else (float("nan"), float("nan"))
     teams = " ".join(f"{med(8 + t)[0]:6.1f}" for t in range(5) if (r[:, 8 + t] > 0).any())
     print(f"  CTA {c}: start {med(0)[0]:5.1f} | raw operands {med(26)[0]:5.1f}, element-wise {med(27)[0]:5.1f}, all {med(1)[0]:5.1f} | teams done {teams} | sweep done {med(4)[0]:6.1f} (max {med(4)[1]:6.1f})"
-          f" | maps (warp 1) {med(3)[0]:6.1f}, CTA barrier {med(2)[0]:6.1f} | backtrack {med(5)[0]:6.1f} (handed down {med(13)[0]:6.1f}) -> {med(6)[0]:6.1f} | output {med(7)[0]:6.1f} (max {med(7)[1]:6.1f})")
+          f" | zero fill waited {med(14)[0]:6.1f}, maps (warp 1) {med(3)[0]:6.1f} (last builder {med(15)[0]:6.1f}), CTA barrier {med(2)[0]:6.1f} | backtrack {med(5)[0]:6.1f} (handed down {med(13)[0]:6.1f}) -> {med(6)[0]:6.1f} | output {med(7)[0]:6.1f} (max {med(7)[1]:6.1f})")
     cyc = lambda k: float(np.median(r[:, k]))
     nb = max(cyc(21), 1.0)
     print(f"         sweep warp, cycles per 32-frame block ({nb:.0f} blocks): waits chunks {cyc(16) / nb:6.0f}, boundary {cyc(17) / nb:6.0f}, credit {cyc(18) / nb:6.0f};"
