@@ -310,6 +310,10 @@ __device__ __forceinline__ int team_contract(const CUtensorMap &tmap_z, const Ge
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_a(zp.empty_a + st * 8u);
         }
+        // the sweep warp has summed the row constants (the ring no longer holds the raw token-side values).
+        // BEFORE the back-pressure wait: with a shallow ring the first round of chunks can already span more
+        // boxes than the ring has, and the sweep -- which frees them -- passes this barrier only with every team
+        if (count == 0) named_sync(kBarAll, g.nteams * tn + 32);
         if (ttid == 0) {
             // back-pressure: the boxes this chunk is stored into must have been swept
             const int bx_last = ((min(u.f_hi, u.f_lo + j * F + F) - 1) >> 5) - u.cb0;
@@ -320,7 +324,6 @@ __device__ __forceinline__ int team_contract(const CUtensorMap &tmap_z, const Ge
         }
         float *sL2 = sL2_base + (count & 1) * g.F_cap;
         if (kMeanOnly && ttid < F) sL2[ttid] = l2;
-        if (count == 0) named_sync(kBarAll, g.nteams * tn + 32);   // the sweep warp has summed the row constants
         named_sync(bar, tn);                                // the ring has room (and the frame sums are there)
         if (worker) {
             const int fb = u.f_lo + j * F;                  // the chunk's first frame

@@ -21,6 +21,10 @@ from conftest import ragged_lengths  # noqa: E402
 from test_fused_gpu import synth_prior, to_dev  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 150.0
+import os
+verbose = os.environ.get('FUZZ_VERBOSE') is not None
+only = int(os.environ['FUZZ_ONLY']) if 'FUZZ_ONLY' in os.environ else None
+repeat = int(os.environ.get('FUZZ_REPEAT', '1'))
 rng = np.random.default_rng(20261018)
 t0 = time.time(); n = 0; bad = 0
 while time.time() - t0 < budget:
@@ -42,10 +46,21 @@ while time.time() - t0 < budget:
             zz[b, int(rng.integers(0, D)), int(rng.integers(0, max(1, t_y[b])))] = float(rng.choice([np.nan, np.inf, -np.inf]))
         args = (args[0], args[1], zz, args[3], args[4])
     lib = pkg._lib.load()
+    if only is not None and n != only:      # FUZZ_ONLY=i: draw everything, run only shape i (FUZZ_REPEAT times)
+        n += 1
+        continue
+    if verbose:     # FUZZ_VERBOSE=1: the shape before it runs and a synchronize after every call (a kernel fault names its shape)
+        print(n, 'B', B, 'D', D, 'T_x', T_x, 'T_y', T_y, 'mean_only', mean_only, 't_x', t_x[:6].tolist(), 't_y', t_y[:6].tolist(), flush=True)
     lib.mas_b200_debug_force_unfused(2)
+    for rep_i in range(repeat - 1):
+        pkg.fused_maximum_path(*args, want_frame_token=True)
+        torch.cuda.synchronize()
+        print('  repeat', rep_i, 'ok', flush=True)
     path, dur, tok = pkg.fused_maximum_path(*args, want_frame_token=True)
+    if verbose: torch.cuda.synchronize(); print('  forced single launch ok', flush=True)
     lib.mas_b200_debug_force_unfused(0)
     path0, dur0, tok0 = pkg.fused_maximum_path(*args, want_frame_token=True)
+    if verbose: torch.cuda.synchronize(); print('  entry ok', flush=True)
     logp = pkg.log_likelihood_matrix(*args[:3])
     k1 = pkg.maximum_path_from_lengths(logp, to_dev(t_x), to_dev(t_y))
     ok = torch.equal(k1, path) and torch.equal(path0, path) and torch.equal(dur0, dur) and torch.equal(tok0, tok)
@@ -59,4 +74,6 @@ while time.time() - t0 < budget:
     n += 1
     if not ok:
         bad += 1; print('FAIL', B, D, T_x, T_y, mean_only, rel, flush=True)
+    if only is not None:
+        break
 print(f'{n} shapes, {bad} failures')

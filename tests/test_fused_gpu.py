@@ -154,6 +154,10 @@ def test_fused_is_length_robust(pkg, oracle, fused_mode):
 @pytest.mark.parametrize("shape", [(4, 80, 200, 1000), (3, 80, 64, 256), (2, 40, 300, 640), (40, 80, 96, 320),
                                    (160, 80, 40, 96),      # more utterances than clusters: several rounds per cluster
                                    (3, 80, 1024, 1536),    # 128-token slices over 8 CTAs, direction bits in the workspace
+                                   # a score ring of 5 boxes under three teams of 48-frame chunks: the first round of chunks
+                                   # spans more boxes than the ring has (the fuzzer's find: the teams' first store used to
+                                   # wait for ring room BEFORE the barrier the sweep -- which frees the room -- waits at)
+                                   (1, 80, 824, 2496),
                                    (5, 33, 10, 52),
                                    # few channels: the contraction outruns the sweep (back-pressure on the score ring) and a
                                    # chunk is fewer z panels than the pipeline holds (a fast warp is a whole chunk ahead)
