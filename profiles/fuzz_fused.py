@@ -25,7 +25,7 @@ import os
 verbose = os.environ.get('FUZZ_VERBOSE') is not None
 only = int(os.environ['FUZZ_ONLY']) if 'FUZZ_ONLY' in os.environ else None
 repeat = int(os.environ.get('FUZZ_REPEAT', '1'))
-rng = np.random.default_rng(20261018)
+rng = np.random.default_rng(int(os.environ.get("FUZZ_SEED", "20261018")))
 t0 = time.time(); n = 0; bad = 0
 while time.time() - t0 < budget:
     big = rng.random() < 0.15

@@ -18,7 +18,8 @@ oracle = entry.load_oracle()
 from conftest import ragged_lengths  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
-rng = np.random.default_rng(4242)
+import os
+rng = np.random.default_rng(int(os.environ.get("FUZZ_SEED", "4242")))
 t0 = time.time()
 n = bad = 0
 while time.time() - t0 < budget:
