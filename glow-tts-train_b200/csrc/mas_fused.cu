@@ -1289,10 +1289,10 @@ static double estimate_us(const Geom &g, int B, int num_sms) {
 // ... and the two kernels back to back: the materialising kernel's rounds of (token tile, chunk)
 // units (16.5 us each on every SM, mas_logp.cu) + kernel (1) (latency floor 41 ns per frame, else
 // ~500 Gcells/s).
-static double estimate_two_kernels_us(int B, int T_x, int T_y) {
+static double estimate_two_kernels_us(int B, int T_x, int T_y, int num_sms) {
     const TileShape t = make_tile_shape(T_x, T_y);
     const double units = (double)B * t.row_tiles * t.nchunks;
-    const double logp_us = ceil(units / 148.0) * 16.5 + 6.0;
+    const double logp_us = ceil(units / (double)num_sms) * 16.5 + 6.0;
     const double cells = (double)B * T_x * T_y;
     // kernel (1): ~500 Gcells/s once every SM streams, else the dependent chain: 41 ns per frame with up to
     // three sweep warps (<= 288 tokens), 53 ns with more (measured: profiles/r2_sweep_k.txt)
@@ -1370,7 +1370,7 @@ int launch_fused(const LogpParams &lp_in, const int32_t *x_len, const int32_t *y
     if (!choose_geom(B, D, T_x, T_y, di.max_smem_optin - 1024, di.num_sms, g)) MAS_FUSED_NO("no slice geometry fits shared memory");
     static const char *mode_env = getenv("MAS_B200_FUSED_MODE");    // "cluster": always the single launch (experiments)
     if (!force && !(mode_env && mode_env[0] == 'c')) {
-        const double one = estimate_us(g, B, di.num_sms), two = estimate_two_kernels_us(B, T_x, T_y);
+        const double one = estimate_us(g, B, di.num_sms), two = estimate_two_kernels_us(B, T_x, T_y, di.num_sms);
         if (debug) fprintf(stderr, "[mas_b200] estimates: single launch %.0f us, two kernels %.0f us\n", one, two);
         if (two < one) MAS_FUSED_NO("the two kernels are estimated faster for this shape");
     }
