@@ -25,7 +25,13 @@
 //     the direction bits, frees
 //     the box (`consumed`, the producers' back-pressure), and drips bulk copies of a zero page into
 //     the dense output on the way.
-//   * backtrack by tokens, CTA K-1 -> 0 over DSMEM; ones, durations, frame -> token by all threads.
+//   * backtrack, CTA K-1 -> 0 over DSMEM.  Short slices (<= 64 tokens): while the sweep runs, the warps
+//     whose contraction is done tabulate per 32-frame block the BLOCK MAP (token at the block's last
+//     frame -> token at the previous block's last frame) and the EXIT TABLE (the same composed all the
+//     way down: the frame where the path leaves the slice); a hop through a CTA is then the entry
+//     block's walk and one look-up, the (token, frame) hand-over an 8-byte st.async onto the next
+//     CTA's mbarrier, and the per-block walks that record the path run one warp per block.  Long
+//     slices walk tokens CTA after CTA like kernel (1).  Ones, durations, frame -> token by all threads.
 // Only the cells the reference's band touches are ever contracted (core.pyx:18): a slice starts at
 // the 32-frame block of its first token and ends where its last token leaves the band.
 //
