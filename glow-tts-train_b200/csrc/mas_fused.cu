@@ -785,6 +785,7 @@ template <int R, bool kDbg>
 __global__ void __launch_bounds__(kThreads, 1)
 mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, LogpParams lp, Geom g) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    ptx::grid_launch_dependents();      // (a following instance may be scheduled from now on; it waits before it touches global memory)
     const int tid = threadIdx.x, lane = tid & 31;
     // broadcast so that the compiler knows the warp index is warp-uniform (see dp_cta)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -831,6 +832,11 @@ mas_fused_kernel(const __grid_constant__ CUtensorMap tmap_z, PathParams pp, Logp
         ptx::fence_proxy_async();
         __syncthreads();
     }
+    // Programmatic dependent launch: when the kernel BEFORE this one in the stream is another instance of
+    // this launch (back-to-back steps), it lets this grid's CTAs take the SMs its own CTAs leave -- they get
+    // as far as here (shared memory only) and then wait for that grid to complete and flush.  After any
+    // other kernel the wait returns at once (the launch was serialised the ordinary way).
+    ptx::grid_dependency_wait();
     long long *dbg = (kDbg && pp.dbg_cycles) ? pp.dbg_cycles + (size_t)blockIdx.x * 32 : nullptr;
     int zseq = 0;                       // z panels this thread's team has consumed so far (mbarrier phases run on)
 
@@ -1257,13 +1263,16 @@ static int launch_r(const CUtensorMap &tmap_z, const PathParams &pp, const LogpP
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = (size_t)g.total;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)g.K;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    static const char *pdl_env = getenv("MAS_B200_PDL");       // experiment hook
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (pdl_env && atoi(pdl_env) == 0) ? 1 : 2;
     // how many clusters the device holds at once (per device and K: the query is not free)
     static std::atomic<int> cache[2][64][9];
     int nc = cache[dbgk][dev & 63][g.K].load();

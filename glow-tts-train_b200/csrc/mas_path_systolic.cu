@@ -29,6 +29,7 @@
 // ranges.  A dedicated warp per CTA zero-fills its slice of the dense output with bulk async
 // copies while the sweep runs; the ones are written last.
 #include <cuda.h>
+#include <cstdlib>
 #include <cudaTypedefs.h>
 
 #include "mas_dp_cta.cuh"
@@ -42,6 +43,9 @@ template <int R, int kThreads, bool kDbg, bool kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
 mas_path_systolic_kernel(const __grid_constant__ CUtensorMap tmap, PathParams p, Plan plan) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    // programmatic dependent launch (mas_fused.cu): back-to-back instances overlap the launch itself
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
     const int K = kCluster ? plan.K : 1;
     dp_cta<R, kDbg, kCluster>(tmap, p, plan, smem, blockIdx.x / K, blockIdx.x);
 }
@@ -103,13 +107,16 @@ static int launch_rt(const CUtensorMap &tmap, const PathParams &p, const Plan &p
     cfg.blockDim = dim3((unsigned)((plan.W + 1) * 32));
     cfg.dynamicSmemBytes = (size_t)plan.total;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)plan.K;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    static const char *pdl_env = getenv("MAS_B200_PDL");       // experiment hook (shared with the single launch)
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (pdl_env && atoi(pdl_env) == 0) ? 1 : 2;
     MAS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmap, p, plan));
     return MAS_OK;
 }
